@@ -1,0 +1,140 @@
+/*
+ * sr_engine.h -- C ABI of the B200 (sm_100a) cosine-similarity + top-K scoring
+ * engine: the drop-in boundary for the hot path of Iamdarika/Spotify_recommender.
+ *
+ * The reference has no FFI: its hot path is reached through the C++ class in
+ * Recommender.h:28-82.  Each entry point below names the reference code it
+ * replaces; sr_recommender.hpp (same directory) re-creates that class on top of
+ * these calls so the reference's main.cpp keeps working unchanged.
+ *
+ * Conventions
+ *   - plain C types only; every call returns 0 on success or an SR_E* code and
+ *     leaves a message readable through sr_engine_last_error().
+ *   - one engine = one CUDA device (one process per GPU); calls on one engine
+ *     are serialised by the caller (the reference is single-threaded, §8b).
+ *   - there is NO CPU fallback: without an sm_100 device create() fails.
+ *   - song ids are 32-bit and GLOBAL: id = id_base + local row, so a row shard
+ *     of a larger store answers with ids of the whole store.
+ *   - results are ordered by (score descending, id ascending); rows shorter
+ *     than k are padded with id -1 / score 0.  Scores are bit-identical to the
+ *     reference's CPU arithmetic (Recommender.cu:256-273).
+ *   - 1 <= k <= 1024.
+ */
+#ifndef SR_ENGINE_H
+#define SR_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR_FEATURE_COUNT 12 /* reference Song.h:12 */
+
+enum {
+    SR_OK = 0,
+    SR_EINVAL = 1,   /* bad argument (null, k <= 0, index out of range ...) */
+    SR_ENODEVICE = 2,/* no usable sm_100 CUDA device                        */
+    SR_ECUDA = 3,    /* a CUDA runtime call or kernel failed                 */
+    SR_ENOMEM = 4,   /* host or device allocation failed                    */
+    SR_ESTATE = 5    /* call made before load_features                      */
+};
+
+typedef struct sr_engine sr_engine;
+
+/* Replaces the device probing / cublasCreate part of Recommender::initialize
+ * (Recommender.cu:117-149).  device < 0 selects the current device. */
+int sr_engine_create(sr_engine **out, int device);
+
+/* Replaces Recommender::~Recommender (Recommender.cu:86-98). */
+void sr_engine_destroy(sr_engine *e);
+
+/* Last error text of this engine ("" if none); e == NULL gives the text of the
+ * last failed create(). */
+const char *sr_engine_last_error(const sr_engine *e);
+
+/* Replaces the pack + upload part of Recommender::initialize
+ * (Recommender.cu:153-175): rows is a HOST dense row-major n x 12 FP32 matrix
+ * (Song::features of every song, Song.h:26).  Builds the device-resident
+ * stores (raw rows + exact norms, and the pre-normalised scan store).  May be
+ * called again to replace the store.  id_base is the global id of row 0. */
+int sr_engine_load_features(sr_engine *e, const float *rows, int64_t n, int64_t id_base);
+
+/* Same, rows already on this engine's device (n x 12, 16-byte aligned). */
+int sr_engine_load_features_device(sr_engine *e, const float *d_rows, int64_t n, int64_t id_base);
+
+/* Recommender::getSongCount (Recommender.h:82). */
+int64_t sr_engine_song_count(const sr_engine *e);
+
+/* Replaces Recommender::recommendByIndex (Recommender.cu:275-318) for a BATCH
+ * of in-store query songs: qidx are global ids owned by this engine; each
+ * query excludes itself by id (Recommender.cu:296).  HOST buffers;
+ * out_idx / out_score are nq x k.  out_score may be NULL. */
+int sr_engine_query_by_index(sr_engine *e, const int32_t *qidx, int nq, int k,
+                             int32_t *out_idx, float *out_score);
+
+/* Same scoring for arbitrary query rows (nq x 12, HOST).  exclude is NULL or nq
+ * global ids to skip (-1: none).  This is what a row shard of a multi-GPU store
+ * is asked: the query row may live on another shard. */
+int sr_engine_query_by_vector(sr_engine *e, const float *qrows, const int32_t *exclude,
+                              int nq, int k, int32_t *out_idx, float *out_score);
+
+/* Device-resident variants: all pointers are device memory of this engine's
+ * device, work is enqueued on `stream` (a cudaStream_t; NULL = the engine's own
+ * stream) and NOT synchronised.  Used by the multi-GPU host (torch owns the
+ * buffers and the NCCL exchange) and by bench.py's kernel-only timing. */
+int sr_engine_query_by_index_dev(sr_engine *e, const int32_t *d_qidx, int nq, int k,
+                                 int32_t *d_out_idx, float *d_out_score, void *stream);
+int sr_engine_query_by_vector_dev(sr_engine *e, const float *d_qrows, const int32_t *d_exclude,
+                                  int nq, int k, int32_t *d_out_idx, float *d_out_score,
+                                  void *stream);
+
+/* Final step of the row-sharded multi-GPU path: merges `parts`
+ * per-shard result lists (parts x nq x k, as gathered by NCCL all-gather; -1
+ * padded) into one list per query in (score desc, id asc) order.  Device
+ * pointers, stream-ordered. */
+int sr_engine_merge_topk_dev(sr_engine *e, const int32_t *d_idx, const float *d_score,
+                             int parts, int nq, int k, int32_t *d_out_idx, float *d_out_score,
+                             void *stream);
+
+/* All-pairs neighbour table (BASELINE config 5): for every owned song with
+ * global id in [q_lo, q_hi) its top-k neighbours, streamed through the same
+ * kernels in batches.  HOST outputs, (q_hi - q_lo) x k. */
+int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k,
+                             int32_t *out_idx, float *out_score);
+
+/* Tunables (DESIGN.md "knobs"):
+ *   "variant"   scan kernel shape, index into the table sr_engine_variant_name() lists
+ *   "qt"        queries per shared-memory tile (1..128)
+ *   "batch"     max queries per internal pass (workspace is sized for it)
+ *   "sample"    threshold-bootstrap sample size per query (0 = off, else power of two <= 4096)
+ *   "profile"   1: bracket every kernel with CUDA events (read with sr_engine_get_timing)
+ *   "reset"     any value: zero the counters and timings below               */
+int sr_engine_set_option(sr_engine *e, const char *key, int64_t value);
+
+/* Counters since create()/reset (synchronises the engine's stream):
+ * "kernel_launches", "queries", "filter_hits", "settles", "rescans", "rescored",
+ * "irregular_songs", "sm_count", "scan_grid", "scan_tile_songs", "device_bytes",
+ * "variant", "qt". */
+int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value);
+
+/* With "profile" on: total device milliseconds and launch count of one kernel
+ * ("prep", "sample", "scan", "finalize", "merge") since the last reset, measured
+ * with CUDA events on the launching stream.  Synchronises that stream. */
+int sr_engine_get_timing(sr_engine *e, const char *kernel, double *ms_total, int64_t *launches);
+
+/* Name of scan-kernel shape i ("S8xT256x2" ...), NULL past the end. */
+const char *sr_engine_variant_name(int i);
+
+/* FP32 pipe microbenchmark on this engine's device, the measured FP32 roofline
+ * denominator.  variant 0: FFMA, 1: packed FFMA2 (fma.rn.f32x2), 2: unfused
+ * FMUL+FADD (the oracle's instruction mix).  Returns TFLOP/s (2 flop per FMA). */
+int sr_engine_measure_fp32(sr_engine *e, int variant, double *tflops);
+
+/* Blocks until everything enqueued on the engine's own stream has finished. */
+int sr_engine_synchronize(sr_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SR_ENGINE_H */

@@ -1,0 +1,198 @@
+// sr_device.cuh -- device-side building blocks of the cosine top-K engine
+// (sm_100a only).  See DESIGN.md for the data layout and the proof sketch of the
+// filter-with-margin + exact re-score scheme.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sr {
+
+constexpr int kF = 12;            // reference Song.h:12 FEATURE_COUNT
+constexpr int kQTMax = 128;       // queries resident in shared memory per CTA
+constexpr int kSortCap = 4096;    // keys sorted per pass by one CTA in finalize / sample
+constexpr int kKMax = 1024;       // largest supported top-K
+constexpr int kRowPad = 36864;    // store rows are padded to a multiple of every tile size
+
+// The fused filter value differs from the oracle's score by at most ~54 u
+// (u = 2^-24, 3.2e-6) for regular rows and queries: DESIGN.md "filter slack".
+// Every filter threshold is the exact running K-th best minus kEps.
+constexpr float kEps = 5.0e-6f;
+// rows / queries whose exact norm is outside [kNormLo, kNormHi] (and not 0) are
+// "irregular": the bound above assumes no under/overflow, so they carry NaN in
+// the normalised store / record, always pass the filter and are scored exactly.
+constexpr float kNormLo = 1.0e-3f;
+constexpr float kNormHi = 1.0e15f;
+
+// candidate not yet scored in the oracle's arithmetic: hi word of the key
+constexpr uint32_t kUnscored = 0xFFFFFFFFu;
+
+// ---- order-preserving key encoding ----------------------------------------
+// key = orderable(score) << 32 | (0xFFFFFFFF - id): larger key == better under
+// (score descending, id ascending).  key 0 is the "no entry" sentinel.
+__host__ __device__ __forceinline__ uint32_t f2ord(float f)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t o)
+{
+    uint32_t u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+constexpr uint32_t kOrdNegInf = 0x007FFFFFu;  // f2ord(-inf)
+
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t id)
+{
+    // +0.0f folds -0 into +0 so that signed zeros tie (oracle compares with ==)
+    return ((uint64_t)f2ord(__fadd_rn(score, 0.0f)) << 32) | (uint64_t)(0xFFFFFFFFu - id);
+}
+__device__ __forceinline__ uint32_t key_id(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
+__device__ __forceinline__ float key_score(uint64_t k) { return ord2f((uint32_t)(k >> 32)); }
+
+// ---- the oracle's arithmetic, instruction for instruction ------------------
+// reference Recommender.cu:263-271: unfused multiply/add in feature order,
+// den = sqrtf(norm) * queryNorm, IEEE divide, std::min/std::max clamp.
+// __fmul_rn/__fadd_rn are never contracted into FMA by nvcc.
+__device__ __forceinline__ float exact_norm(const float *f)
+{
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kF; ++j) acc = __fadd_rn(acc, __fmul_rn(f[j], f[j]));
+    return __fsqrt_rn(acc);
+}
+
+__device__ __forceinline__ float exact_finish(float dot, float nf, float qn)
+{
+    float den = __fmul_rn(nf, qn);
+    float s = 0.0f;
+    if (den > 1e-8f) {
+        s = __fdiv_rn(dot, den);
+        s = (s < 1.0f) ? s : 1.0f;     // std::min(1.0f, s)
+        s = (-1.0f < s) ? s : -1.0f;   // std::max(-1.0f, s)
+    }
+    return s;
+}
+
+__device__ __forceinline__ float exact_score(const float *f, float nf, const float *q, float qn)
+{
+    float dot = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kF; ++j) dot = __fadd_rn(dot, __fmul_rn(q[j], f[j]));
+    return exact_finish(dot, nf, qn);
+}
+
+__device__ __forceinline__ void load_row12(const float *base, int64_t row, float *out)
+{
+    const float4 *p = reinterpret_cast<const float4 *>(base) + row * 3;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+    out[8] = c.x; out[9] = c.y; out[10] = c.z; out[11] = c.w;
+}
+
+// ---- block-wide bitonic sort, descending, of L (power of two) 64-bit keys ----
+template <int THREADS>
+__device__ __forceinline__ void bitonic_desc(uint64_t *s, int L)
+{
+    for (int k2 = 2; k2 <= L; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < L; i += THREADS) {
+                int p = i ^ j;
+                if (p > i) {
+                    uint64_t a = s[i], b = s[p];
+                    bool desc = ((i & k2) == 0);
+                    if ((a < b) == desc) { s[i] = b; s[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int THREADS>
+__device__ __forceinline__ void bitonic_desc_u32(uint32_t *s, int L)
+{
+    for (int k2 = 2; k2 <= L; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < L; i += THREADS) {
+                int p = i ^ j;
+                if (p > i) {
+                    uint32_t a = s[i], b = s[p];
+                    bool desc = ((i & k2) == 0);
+                    if ((a < b) == desc) { s[i] = b; s[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ---- warp-cooperative radix select -------------------------------------------
+// Finds the want-th largest 32-bit value among w(i) for i in [0,cnt) that pass
+// `match(i)`; returns it and the rank still wanted inside its tie group through
+// *rank_in_ties.  hist: 256 counters of shared memory owned by this warp.
+template <typename WordFn>
+__device__ __forceinline__ uint32_t warp_radix_select(int cnt, int want, uint32_t *hist, WordFn word,
+                                                      int *rank_in_ties)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t prefix = 0, mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+        __syncwarp();
+        for (int i = lane; i < cnt; i += 32) {
+            uint32_t w;
+            if (word(i, &w) && (w & mask) == prefix) atomicAdd(&hist[(w >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        uint32_t local[8];
+        uint32_t tot = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { local[b] = hist[lane * 8 + b]; tot += local[b]; }
+        uint32_t suf = tot;  // inclusive suffix sum over lanes (high digits first)
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t v = __shfl_down_sync(0xffffffffu, suf, off);
+            if (lane + off < 32) suf += v;
+        }
+        uint32_t above = suf - tot;
+        bool mine = (above < (uint32_t)want) && ((uint32_t)want <= suf);
+        uint32_t digit = 0, nw = 0;
+        if (mine) {
+            uint32_t c = above;
+#pragma unroll
+            for (int b = 7; b >= 0; --b) {
+                if (c < (uint32_t)want && (uint32_t)want <= c + local[b]) { digit = lane * 8 + b; nw = want - c; }
+                c += local[b];
+            }
+        }
+        uint32_t who = __ballot_sync(0xffffffffu, mine);
+        int src = who ? (__ffs(who) - 1) : 0;
+        digit = __shfl_sync(0xffffffffu, digit, src);
+        nw = __shfl_sync(0xffffffffu, nw, src);
+        prefix |= digit << shift;
+        mask |= 255u << shift;
+        want = (int)nw;
+        __syncwarp();
+    }
+    *rank_in_ties = want;
+    return prefix;
+}
+
+}  // namespace sr

@@ -1,0 +1,719 @@
+// sr_engine.cu -- host side of the C ABI declared in include/sr_engine.h: device
+// store management, batch workspace, kernel launches.  sm_100a only; there is no
+// CPU fallback anywhere in this file (north_star (1)).
+#include "../../include/sr_engine.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sr_aux.cuh"
+#include "sr_scan.cuh"
+
+namespace {
+
+using namespace sr;
+
+thread_local std::string g_create_error;
+
+// ---- scan kernel shapes --------------------------------------------------------
+typedef cudaError_t (*ScanLaunch)(const ScanArgs &, int grid, size_t smem, cudaStream_t st);
+typedef cudaError_t (*ScanOcc)(int *ctas_per_sm, size_t smem);
+
+template <int S, int T, int M, bool D>
+cudaError_t launch_scan(const ScanArgs &a, int grid, size_t smem, cudaStream_t st)
+{
+    auto k = scan_kernel<S, T, M, D>;
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k<<<grid, T, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <int S, int T, int M, bool D>
+cudaError_t occ_scan(int *ctas, size_t smem)
+{
+    auto k = scan_kernel<S, T, M, D>;
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k, T, smem);
+}
+
+struct Variant {
+    const char *name;
+    int S, threads;
+    ScanLaunch launch;
+    ScanOcc occ;
+};
+#define SR_VARIANT(S, T, M, D) \
+    {"S" #S "xT" #T "x" #M "-" #D, S, T, launch_scan<S, T, M, D>, occ_scan<S, T, M, D>}
+const Variant kVariants[] = {
+    SR_VARIANT(8, 256, 2, false),
+    SR_VARIANT(8, 256, 2, true),
+    SR_VARIANT(8, 512, 1, false),
+    SR_VARIANT(8, 512, 1, true),
+    SR_VARIANT(8, 384, 1, false),
+    SR_VARIANT(8, 384, 1, true),
+    SR_VARIANT(4, 256, 4, true),
+    SR_VARIANT(12, 384, 1, true),
+};
+constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+
+enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kNumKernels };
+const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge"};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct sr_engine {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // store
+    float *d_raw = nullptr, *d_hat = nullptr, *d_nf = nullptr;
+    int64_t n = 0, n_pad = 0;
+    int32_t id_base = 0;
+    int64_t irregular = 0;
+
+    // options
+    int variant = 0;
+    int qt_opt = kQTMax;
+    int batch = 8192;
+    int sample = -1;  // -1: automatic
+    bool profile = false;
+
+    // batch workspace (grow-only)
+    DevBuf qraw, qn, qhat, excl, gbest, pool_cnt, pool, cta_buf, out_idx, out_score, qin, exin;
+    unsigned long long *d_stats = nullptr;  // [8]
+    unsigned long long *d_irregular = nullptr;
+    int32_t *d_flag = nullptr;
+    void *h_pin = nullptr;
+    size_t h_pin_cap = 0;
+    int scan_grid = 0;
+
+    // counters
+    int64_t launches = 0, queries = 0;
+    struct Timed {
+        cudaEvent_t a, b;
+        int kernel;
+    };
+    std::vector<Timed> pending;
+    double ms_total[kNumKernels] = {0, 0, 0, 0, 0};
+    int64_t ms_count[kNumKernels] = {0, 0, 0, 0, 0};
+    int64_t device_bytes = 0;
+};
+
+namespace {
+
+int fail(sr_engine *e, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define SR_CUDA(call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t err_ = (call);                                                                          \
+        if (err_ != cudaSuccess)                                                                            \
+            return fail(e, err_ == cudaErrorMemoryAllocation ? SR_ENOMEM : SR_ECUDA, "%s failed: %s (%s:%d)", \
+                        #call, cudaGetErrorString(err_), __FILE__, __LINE__);                               \
+    } while (0)
+
+int ensure(sr_engine *e, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return SR_OK;
+    if (b.p) {
+        SR_CUDA(cudaStreamSynchronize(e->stream));
+        SR_CUDA(cudaFree(b.p));
+        e->device_bytes -= (int64_t)b.cap;
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    SR_CUDA(cudaMalloc(&b.p, want));
+    b.cap = want;
+    e->device_bytes += (int64_t)want;
+    return SR_OK;
+}
+
+int ensure_pinned(sr_engine *e, size_t bytes)
+{
+    if (bytes <= e->h_pin_cap) return SR_OK;
+    if (e->h_pin) {
+        SR_CUDA(cudaStreamSynchronize(e->stream));
+        SR_CUDA(cudaFreeHost(e->h_pin));
+        e->h_pin = nullptr;
+        e->h_pin_cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    SR_CUDA(cudaMallocHost(&e->h_pin, want));
+    e->h_pin_cap = want;
+    return SR_OK;
+}
+
+struct Scope {  // event bracket around one kernel when profiling
+    sr_engine *e;
+    cudaStream_t st;
+    int kernel;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Scope(sr_engine *e_, cudaStream_t st_, int k) : e(e_), st(st_), kernel(k)
+    {
+        ++e->launches;
+        if (!e->profile) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+        cudaEventRecord(a, st);
+    }
+    ~Scope()
+    {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        e->pending.push_back({a, b, kernel});
+    }
+};
+
+int resolve_timings(sr_engine *e)
+{
+    for (auto &t : e->pending) {
+        SR_CUDA(cudaEventSynchronize(t.b));
+        float ms = 0.f;
+        SR_CUDA(cudaEventElapsedTime(&ms, t.a, t.b));
+        e->ms_total[t.kernel] += ms;
+        e->ms_count[t.kernel] += 1;
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    e->pending.clear();
+    return SR_OK;
+}
+
+int pow2_floor(int64_t v)
+{
+    int p = 1;
+    while ((int64_t)p * 2 <= v) p *= 2;
+    return p;
+}
+
+int build_store(sr_engine *e)
+{
+    // d_raw holds n rows; pad rows are already zero
+    SR_CUDA(cudaMemsetAsync(e->d_irregular, 0, 8, e->stream));
+    const int threads = 256;
+    const int64_t blocks = (e->n_pad + threads - 1) / threads;
+    build_store_kernel<<<(unsigned)blocks, threads, 0, e->stream>>>(e->d_raw, e->n, e->n_pad, e->d_nf, e->d_hat,
+                                                                     e->d_irregular);
+    SR_CUDA(cudaGetLastError());
+    ++e->launches;
+    unsigned long long irr = 0;
+    SR_CUDA(cudaMemcpyAsync(&irr, e->d_irregular, 8, cudaMemcpyDeviceToHost, e->stream));
+    SR_CUDA(cudaStreamSynchronize(e->stream));
+    e->irregular = (int64_t)irr;
+    return SR_OK;
+}
+
+int alloc_store(sr_engine *e, int64_t n, int64_t id_base)
+{
+    if (n <= 0) return fail(e, SR_EINVAL, "load_features: n must be positive (got %lld)", (long long)n);
+    if (id_base < 0 || id_base + n > 0x7fffffffLL)
+        return fail(e, SR_EINVAL, "load_features: ids [%lld, %lld) do not fit 32 bits", (long long)id_base,
+                    (long long)(id_base + n));
+    SR_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->d_raw) {
+        cudaFree(e->d_raw); cudaFree(e->d_hat); cudaFree(e->d_nf);
+        e->device_bytes -= e->n_pad * (int64_t)(2 * kF + 1) * 4;
+        e->d_raw = e->d_hat = e->d_nf = nullptr;
+        e->n = e->n_pad = 0;
+    }
+    const int64_t n_pad = (n + kRowPad - 1) / kRowPad * kRowPad;
+    SR_CUDA(cudaMalloc(&e->d_raw, (size_t)n_pad * kF * 4));
+    SR_CUDA(cudaMalloc(&e->d_hat, (size_t)n_pad * kF * 4));
+    SR_CUDA(cudaMalloc(&e->d_nf, (size_t)n_pad * 4));
+    e->device_bytes += n_pad * (int64_t)(2 * kF + 1) * 4;
+    e->n = n;
+    e->n_pad = n_pad;
+    e->id_base = (int32_t)id_base;
+    SR_CUDA(cudaMemsetAsync(e->d_raw + (size_t)n * kF, 0, (size_t)(n_pad - n) * kF * 4, e->stream));
+    return SR_OK;
+}
+
+// The constant bank holding the current group's normalised queries is one per device
+// (per CUDA context), shared by every engine of the process on that device: a group's
+// upload is ordered behind the last scan that read the bank, on whichever stream it ran.
+std::mutex g_bank_mutex;
+cudaEvent_t g_bank_event[64] = {nullptr};
+
+// One internal pass: nq <= e->batch queries, everything on device, stream-ordered.
+int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const int32_t *d_excl, int nq, int K,
+             int32_t *d_out_idx, float *d_out_score, cudaStream_t st)
+{
+    const Variant &v = kVariants[e->variant];
+    const int TS = v.S * v.threads;
+    const int warps = v.threads / 32;
+    const int n_tiles = (int)((e->n + TS - 1) / TS);
+    // query groups (what fits the constant bank), evenly filled; then query tiles inside a group
+    const int groups = (nq + kConstQueries - 1) / kConstQueries;
+    const int gsize = (nq + groups - 1) / groups;
+    const int qt_cap = std::max(1, std::min(e->qt_opt, kQTMax));
+    const int nqt0 = (gsize + qt_cap - 1) / qt_cap;
+    const int qt = (gsize + nqt0 - 1) / nqt0;
+    const int nqt = (gsize + qt - 1) / qt;
+    const size_t smem = scan_smem_bytes(qt, warps);
+    int ctas = 0;
+    SR_CUDA(v.occ(&ctas, smem));
+    if (ctas < 1) return fail(e, SR_ECUDA, "scan kernel %s does not fit one SM (smem %zu)", v.name, smem);
+    const int64_t units = (int64_t)nqt * n_tiles;
+    const int grid = (int)std::min<int64_t>((int64_t)e->sm_count * ctas, units);
+    e->scan_grid = grid;
+    const int bufcap = (std::max(2 * K, K + 256) + 31) / 32 * 32;
+    const int prune_at = K + (bufcap - K) / 2;
+    const int segs = scan_segs(grid, nqt);
+
+    int rc;
+    if ((rc = ensure(e, e->qraw, (size_t)nq * kF * 4))) return rc;
+    if ((rc = ensure(e, e->qn, (size_t)nq * 4))) return rc;
+    if ((rc = ensure(e, e->qhat, (size_t)nq * kF * 4))) return rc;
+    if ((rc = ensure(e, e->excl, (size_t)nq * 4))) return rc;
+    if ((rc = ensure(e, e->gbest, (size_t)nq * 4))) return rc;
+    if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
+    if ((rc = ensure(e, e->pool, (size_t)nq * segs * K * 8))) return rc;
+    if ((rc = ensure(e, e->cta_buf, (size_t)grid * qt * bufcap * 8))) return rc;
+
+    {
+        PrepArgs p;
+        p.raw_store = e->d_raw; p.n = e->n; p.id_base = e->id_base;
+        p.qidx = d_qidx; p.qrows_in = d_qrows; p.excl_in = d_excl; p.nq = nq;
+        p.qraw = (float *)e->qraw.p; p.qn = (float *)e->qn.p; p.qhat = (float *)e->qhat.p;
+        p.excl = (int32_t *)e->excl.p; p.pool_cnt = (int32_t *)e->pool_cnt.p;
+        p.g_best = (uint32_t *)e->gbest.p; p.bad_index = e->d_flag;
+        Scope sc(e, st, kPrep);
+        prep_queries_kernel<<<(nq + 127) / 128, 128, 0, st>>>(p);
+        SR_CUDA(cudaGetLastError());
+    }
+    // threshold bootstrap
+    int m = e->sample;
+    if (m < 0) m = std::min(kSortCap, std::max(1024, pow2_floor((int64_t)K * 32)));
+    if (m > 0) {
+        m = std::min(m, pow2_floor(e->n / 4));  // only worth it on stores much larger than the sample
+        if (m >= 2 * K && m >= 64) {
+            SampleArgs s;
+            s.raw = e->d_raw; s.nf = e->d_nf; s.n = e->n; s.id_base = e->id_base;
+            s.qraw = (float *)e->qraw.p; s.qn = (float *)e->qn.p; s.exclude = (int32_t *)e->excl.p;
+            s.nq = nq; s.m = m; s.K = K; s.g_best = (uint32_t *)e->gbest.p;
+            Scope sc(e, st, kSample);
+            sample_threshold_kernel<256><<<nq, 256, 0, st>>>(s);
+            SR_CUDA(cudaGetLastError());
+        }
+    }
+    for (int g0 = 0; g0 < nq; g0 += gsize) {
+        const int gq = std::min(gsize, nq - g0);
+        ScanArgs a;
+        a.hat = e->d_hat; a.raw = e->d_raw; a.nf = e->d_nf; a.n = e->n; a.id_base = e->id_base;
+        a.n_tiles = n_tiles;
+        a.qraw = (float *)e->qraw.p + (size_t)g0 * kF; a.qn = (float *)e->qn.p + g0;
+        a.exclude = (int32_t *)e->excl.p + g0; a.nq = gq; a.qt = qt;
+        a.K = K; a.prune_at = prune_at; a.bufcap = bufcap;
+        a.cta_buf = (uint64_t *)e->cta_buf.p; a.g_best = (uint32_t *)e->gbest.p + g0;
+        a.pool = (uint64_t *)e->pool.p + (size_t)g0 * segs * K; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
+        a.segs = segs;
+        a.stats = e->d_stats;
+        const int gnqt = (gq + qt - 1) / qt;
+        const int ggrid = (int)std::min<int64_t>(grid, (int64_t)gnqt * n_tiles);
+        std::lock_guard<std::mutex> lock(g_bank_mutex);
+        cudaEvent_t &ev = g_bank_event[e->device & 63];
+        if (!ev) SR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        else SR_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        SR_CUDA(cudaMemcpyToSymbolAsync(c_qhat, (const float *)e->qhat.p + (size_t)g0 * kF, (size_t)gq * kF * 4, 0,
+                                        cudaMemcpyDeviceToDevice, st));
+        {
+            Scope sc(e, st, kScan);
+            SR_CUDA(v.launch(a, ggrid, smem, st));
+        }
+        SR_CUDA(cudaEventRecord(ev, st));
+    }
+    {
+        FinalArgs f;
+        f.pool = (uint64_t *)e->pool.p; f.pool_cnt = (int32_t *)e->pool_cnt.p;
+        f.nq = nq; f.K = K; f.segs = segs; f.out_idx = d_out_idx; f.out_score = d_out_score;
+        Scope sc(e, st, kFinalize);
+        finalize_kernel<256><<<nq, 256, 0, st>>>(f);
+        SR_CUDA(cudaGetLastError());
+    }
+    e->queries += nq;
+    return SR_OK;
+}
+
+int check_query_args(sr_engine *e, const void *q, int nq, int k, const void *out_idx)
+{
+    if (!e) return SR_EINVAL;
+    if (!e->d_raw) return fail(e, SR_ESTATE, "no store loaded: call sr_engine_load_features first");
+    if (!q || !out_idx) return fail(e, SR_EINVAL, "null query or output pointer");
+    if (nq <= 0) return fail(e, SR_EINVAL, "nq must be positive (got %d)", nq);
+    if (k <= 0 || k > kKMax) return fail(e, SR_EINVAL, "k must be in [1, %d] (got %d)", kKMax, k);
+    return SR_OK;
+}
+
+int run_device(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const int32_t *d_excl, int nq, int k,
+               int32_t *d_out_idx, float *d_out_score, cudaStream_t st)
+{
+    for (int done = 0; done < nq; done += e->batch) {
+        const int cur = std::min(e->batch, nq - done);
+        int rc = run_pass(e, d_qidx ? d_qidx + done : nullptr, d_qrows ? d_qrows + (size_t)done * kF : nullptr,
+                          d_excl ? d_excl + done : nullptr, cur, k, d_out_idx + (size_t)done * k,
+                          d_out_score ? d_out_score + (size_t)done * k : nullptr, st);
+        if (rc) return rc;
+    }
+    return SR_OK;
+}
+
+// host-buffer front end shared by query_by_index / query_by_vector
+int run_host(sr_engine *e, const int32_t *qidx, const float *qrows, const int32_t *exclude, int nq, int k,
+             int32_t *out_idx, float *out_score)
+{
+    const size_t in_q = qidx ? (size_t)nq * 4 : (size_t)nq * kF * 4;
+    const size_t in_x = exclude ? (size_t)nq * 4 : 0;
+    const size_t out_i = (size_t)nq * k * 4;
+    const size_t out_s = out_score ? (size_t)nq * k * 4 : 0;
+    int rc;
+    if ((rc = ensure_pinned(e, in_q + in_x + out_i + out_s))) return rc;
+    if ((rc = ensure(e, e->qin, in_q))) return rc;
+    if (in_x && (rc = ensure(e, e->exin, in_x))) return rc;
+    if ((rc = ensure(e, e->out_idx, out_i))) return rc;
+    if (out_s && (rc = ensure(e, e->out_score, out_s))) return rc;
+    char *pin = (char *)e->h_pin;
+    memcpy(pin, qidx ? (const void *)qidx : (const void *)qrows, in_q);
+    if (in_x) memcpy(pin + in_q, exclude, in_x);
+    SR_CUDA(cudaMemcpyAsync(e->qin.p, pin, in_q, cudaMemcpyHostToDevice, e->stream));
+    if (in_x) SR_CUDA(cudaMemcpyAsync(e->exin.p, pin + in_q, in_x, cudaMemcpyHostToDevice, e->stream));
+    SR_CUDA(cudaMemsetAsync(e->d_flag, 0, 4, e->stream));
+    rc = run_device(e, qidx ? (int32_t *)e->qin.p : nullptr, qidx ? nullptr : (float *)e->qin.p,
+                    in_x ? (int32_t *)e->exin.p : nullptr, nq, k, (int32_t *)e->out_idx.p,
+                    out_s ? (float *)e->out_score.p : nullptr, e->stream);
+    if (rc) return rc;
+    char *pout = pin + in_q + in_x;
+    SR_CUDA(cudaMemcpyAsync(pout, e->out_idx.p, out_i, cudaMemcpyDeviceToHost, e->stream));
+    if (out_s) SR_CUDA(cudaMemcpyAsync(pout + out_i, e->out_score.p, out_s, cudaMemcpyDeviceToHost, e->stream));
+    SR_CUDA(cudaStreamSynchronize(e->stream));
+    memcpy(out_idx, pout, out_i);
+    if (out_s) memcpy(out_score, pout + out_i, out_s);
+    return SR_OK;
+}
+
+__global__ void iota_kernel(int32_t *out, int32_t start, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = start + i;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sr_engine_create(sr_engine **out, int device)
+{
+    sr_engine *e = nullptr;
+    if (!out) return fail(nullptr, SR_EINVAL, "create: null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return fail(nullptr, SR_ENODEVICE, "no CUDA device: %s (this engine has no CPU fallback)",
+                    err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) return fail(nullptr, SR_ENODEVICE, "device %d out of range (%d present)", device, count);
+    cudaDeviceProp prop;
+    if ((err = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, SR_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(err));
+    if (prop.major != 10)
+        return fail(nullptr, SR_ENODEVICE, "device %d (%s) is sm_%d%d; this engine is built for sm_100a only", device,
+                    prop.name, prop.major, prop.minor);
+    if ((err = cudaSetDevice(device)) != cudaSuccess)
+        return fail(nullptr, SR_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(err));
+    e = new sr_engine();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (err = cudaMalloc(&e->d_stats, 8 * 8)) != cudaSuccess || (err = cudaMalloc(&e->d_irregular, 8)) != cudaSuccess ||
+        (err = cudaMalloc(&e->d_flag, 4)) != cudaSuccess || (err = cudaMemset(e->d_stats, 0, 64)) != cudaSuccess ||
+        (err = cudaMemset(e->d_flag, 0, 4)) != cudaSuccess) {
+        int rc = fail(nullptr, SR_ECUDA, "engine setup: %s", cudaGetErrorString(err));
+        sr_engine_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return SR_OK;
+}
+
+void sr_engine_destroy(sr_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto &t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->pool_cnt, &e->pool,
+                      &e->cta_buf, &e->out_idx, &e->out_score, &e->qin, &e->exin};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (e->d_raw) cudaFree(e->d_raw);
+    if (e->d_hat) cudaFree(e->d_hat);
+    if (e->d_nf) cudaFree(e->d_nf);
+    if (e->d_stats) cudaFree(e->d_stats);
+    if (e->d_irregular) cudaFree(e->d_irregular);
+    if (e->d_flag) cudaFree(e->d_flag);
+    if (e->h_pin) cudaFreeHost(e->h_pin);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char *sr_engine_last_error(const sr_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int sr_engine_load_features(sr_engine *e, const float *rows, int64_t n, int64_t id_base)
+{
+    if (!e) return SR_EINVAL;
+    if (!rows) return fail(e, SR_EINVAL, "load_features: null rows");
+    SR_CUDA(cudaSetDevice(e->device));
+    int rc = alloc_store(e, n, id_base);
+    if (rc) return rc;
+    SR_CUDA(cudaMemcpyAsync(e->d_raw, rows, (size_t)n * kF * 4, cudaMemcpyHostToDevice, e->stream));
+    return build_store(e);
+}
+
+int sr_engine_load_features_device(sr_engine *e, const float *d_rows, int64_t n, int64_t id_base)
+{
+    if (!e) return SR_EINVAL;
+    if (!d_rows) return fail(e, SR_EINVAL, "load_features_device: null rows");
+    SR_CUDA(cudaSetDevice(e->device));
+    int rc = alloc_store(e, n, id_base);
+    if (rc) return rc;
+    SR_CUDA(cudaMemcpyAsync(e->d_raw, d_rows, (size_t)n * kF * 4, cudaMemcpyDeviceToDevice, e->stream));
+    return build_store(e);
+}
+
+int64_t sr_engine_song_count(const sr_engine *e) { return e ? e->n : 0; }
+
+int sr_engine_query_by_index(sr_engine *e, const int32_t *qidx, int nq, int k, int32_t *out_idx, float *out_score)
+{
+    int rc = check_query_args(e, qidx, nq, k, out_idx);
+    if (rc) return rc;
+    for (int i = 0; i < nq; ++i) {
+        const int64_t local = (int64_t)qidx[i] - e->id_base;
+        if (local < 0 || local >= e->n)
+            return fail(e, SR_EINVAL, "query %d: song id %d is not in this store [%d, %lld)", i, qidx[i], e->id_base,
+                        (long long)(e->id_base + e->n));
+    }
+    SR_CUDA(cudaSetDevice(e->device));
+    return run_host(e, qidx, nullptr, nullptr, nq, k, out_idx, out_score);
+}
+
+int sr_engine_query_by_vector(sr_engine *e, const float *qrows, const int32_t *exclude, int nq, int k,
+                              int32_t *out_idx, float *out_score)
+{
+    int rc = check_query_args(e, qrows, nq, k, out_idx);
+    if (rc) return rc;
+    SR_CUDA(cudaSetDevice(e->device));
+    return run_host(e, nullptr, qrows, exclude, nq, k, out_idx, out_score);
+}
+
+int sr_engine_query_by_index_dev(sr_engine *e, const int32_t *d_qidx, int nq, int k, int32_t *d_out_idx,
+                                 float *d_out_score, void *stream)
+{
+    int rc = check_query_args(e, d_qidx, nq, k, d_out_idx);
+    if (rc) return rc;
+    SR_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    return run_device(e, d_qidx, nullptr, nullptr, nq, k, d_out_idx, d_out_score, st);
+}
+
+int sr_engine_query_by_vector_dev(sr_engine *e, const float *d_qrows, const int32_t *d_exclude, int nq, int k,
+                                  int32_t *d_out_idx, float *d_out_score, void *stream)
+{
+    int rc = check_query_args(e, d_qrows, nq, k, d_out_idx);
+    if (rc) return rc;
+    SR_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    return run_device(e, nullptr, d_qrows, d_exclude, nq, k, d_out_idx, d_out_score, st);
+}
+
+int sr_engine_merge_topk_dev(sr_engine *e, const int32_t *d_idx, const float *d_score, int parts, int nq, int k,
+                             int32_t *d_out_idx, float *d_out_score, void *stream)
+{
+    if (!e) return SR_EINVAL;
+    if (!d_idx || !d_score || !d_out_idx) return fail(e, SR_EINVAL, "merge: null pointer");
+    if (parts <= 0 || nq <= 0 || k <= 0 || k > kKMax) return fail(e, SR_EINVAL, "merge: bad parts/nq/k");
+    SR_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    Scope sc(e, st, kMerge);
+    merge_parts_kernel<256><<<nq, 256, 0, st>>>(d_idx, d_score, parts, nq, k, d_out_idx, d_out_score);
+    SR_CUDA(cudaGetLastError());
+    return SR_OK;
+}
+
+int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k, int32_t *out_idx, float *out_score)
+{
+    if (!e) return SR_EINVAL;
+    if (!e->d_raw) return fail(e, SR_ESTATE, "no store loaded: call sr_engine_load_features first");
+    if (!out_idx) return fail(e, SR_EINVAL, "all_pairs: null output");
+    if (k <= 0 || k > kKMax) return fail(e, SR_EINVAL, "k must be in [1, %d] (got %d)", kKMax, k);
+    if (q_lo < e->id_base || q_hi > e->id_base + e->n || q_lo >= q_hi)
+        return fail(e, SR_EINVAL, "all_pairs: [%lld, %lld) is not inside this store", (long long)q_lo, (long long)q_hi);
+    SR_CUDA(cudaSetDevice(e->device));
+    const int B = e->batch;
+    int rc;
+    if ((rc = ensure(e, e->qin, (size_t)B * 4))) return rc;
+    if ((rc = ensure(e, e->out_idx, (size_t)B * k * 4))) return rc;
+    if (out_score && (rc = ensure(e, e->out_score, (size_t)B * k * 4))) return rc;
+    if ((rc = ensure_pinned(e, (size_t)B * k * 8))) return rc;
+    for (int64_t lo = q_lo; lo < q_hi; lo += B) {
+        const int cur = (int)std::min<int64_t>(B, q_hi - lo);
+        iota_kernel<<<(cur + 255) / 256, 256, 0, e->stream>>>((int32_t *)e->qin.p, (int32_t)lo, cur);
+        SR_CUDA(cudaGetLastError());
+        ++e->launches;
+        rc = run_pass(e, (int32_t *)e->qin.p, nullptr, nullptr, cur, k, (int32_t *)e->out_idx.p,
+                      out_score ? (float *)e->out_score.p : nullptr, e->stream);
+        if (rc) return rc;
+        char *pin = (char *)e->h_pin;
+        const size_t bytes = (size_t)cur * k * 4;
+        SR_CUDA(cudaMemcpyAsync(pin, e->out_idx.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+        if (out_score) SR_CUDA(cudaMemcpyAsync(pin + bytes, e->out_score.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+        SR_CUDA(cudaStreamSynchronize(e->stream));
+        memcpy(out_idx + (size_t)(lo - q_lo) * k, pin, bytes);
+        if (out_score) memcpy(out_score + (size_t)(lo - q_lo) * k, pin + bytes, bytes);
+    }
+    return SR_OK;
+}
+
+int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
+{
+    if (!e || !key) return SR_EINVAL;
+    if (!strcmp(key, "variant")) {
+        if (value < 0 || value >= kNumVariants) return fail(e, SR_EINVAL, "variant must be in [0, %d)", kNumVariants);
+        e->variant = (int)value;
+    } else if (!strcmp(key, "qt")) {
+        if (value < 1 || value > kQTMax) return fail(e, SR_EINVAL, "qt must be in [1, %d]", kQTMax);
+        e->qt_opt = (int)value;
+    } else if (!strcmp(key, "batch")) {
+        if (value < 1 || value > (1 << 20)) return fail(e, SR_EINVAL, "batch must be in [1, 2^20]");
+        e->batch = (int)value;
+    } else if (!strcmp(key, "sample")) {
+        if (value > kSortCap || (value > 0 && (value & (value - 1))))
+            return fail(e, SR_EINVAL, "sample must be 0, negative (auto) or a power of two <= %d", kSortCap);
+        e->sample = (int)value;
+    } else if (!strcmp(key, "profile")) {
+        e->profile = value != 0;
+    } else if (!strcmp(key, "reset")) {
+        SR_CUDA(cudaSetDevice(e->device));
+        SR_CUDA(cudaStreamSynchronize(e->stream));
+        int rc = resolve_timings(e);
+        if (rc) return rc;
+        SR_CUDA(cudaMemset(e->d_stats, 0, 64));
+        e->launches = e->queries = 0;
+        for (int i = 0; i < kNumKernels; ++i) { e->ms_total[i] = 0; e->ms_count[i] = 0; }
+    } else {
+        return fail(e, SR_EINVAL, "unknown option '%s'", key);
+    }
+    return SR_OK;
+}
+
+int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value)
+{
+    if (!e || !key || !value) return SR_EINVAL;
+    SR_CUDA(cudaSetDevice(e->device));
+    static const char *const dev_keys[] = {"filter_hits", "settles", "rescans", "rescored"};
+    for (int i = 0; i < 4; ++i) {
+        if (!strcmp(key, dev_keys[i])) {
+            unsigned long long h[8];
+            SR_CUDA(cudaStreamSynchronize(e->stream));
+            SR_CUDA(cudaMemcpy(h, e->d_stats, 64, cudaMemcpyDeviceToHost));
+            *value = (int64_t)h[i];
+            return SR_OK;
+        }
+    }
+    if (!strcmp(key, "kernel_launches")) *value = e->launches;
+    else if (!strcmp(key, "queries")) *value = e->queries;
+    else if (!strcmp(key, "irregular_songs")) *value = e->irregular;
+    else if (!strcmp(key, "sm_count")) *value = e->sm_count;
+    else if (!strcmp(key, "scan_grid")) *value = e->scan_grid;
+    else if (!strcmp(key, "scan_tile_songs")) *value = kVariants[e->variant].S * kVariants[e->variant].threads;
+    else if (!strcmp(key, "device_bytes")) *value = e->device_bytes;
+    else if (!strcmp(key, "variant")) *value = e->variant;
+    else if (!strcmp(key, "qt")) *value = e->qt_opt;
+    else return fail(e, SR_EINVAL, "unknown stat '%s'", key);
+    return SR_OK;
+}
+
+int sr_engine_get_timing(sr_engine *e, const char *kernel, double *ms_total, int64_t *launches)
+{
+    if (!e || !kernel || !ms_total) return SR_EINVAL;
+    SR_CUDA(cudaSetDevice(e->device));
+    int rc = resolve_timings(e);
+    if (rc) return rc;
+    for (int i = 0; i < kNumKernels; ++i) {
+        if (!strcmp(kernel, kKernelNames[i])) {
+            *ms_total = e->ms_total[i];
+            if (launches) *launches = e->ms_count[i];
+            return SR_OK;
+        }
+    }
+    return fail(e, SR_EINVAL, "unknown kernel '%s'", kernel);
+}
+
+const char *sr_engine_variant_name(int i) { return (i >= 0 && i < kNumVariants) ? kVariants[i].name : nullptr; }
+
+int sr_engine_measure_fp32(sr_engine *e, int variant, double *tflops)
+{
+    if (!e || !tflops) return SR_EINVAL;
+    if (variant < 0 || variant > 2) return fail(e, SR_EINVAL, "fp32 variant must be 0, 1 or 2");
+    SR_CUDA(cudaSetDevice(e->device));
+    float *d_out = nullptr;
+    SR_CUDA(cudaMalloc(&d_out, 4));
+    const int iters = 20000, grid = e->sm_count * 8;
+    cudaEvent_t a, b;
+    SR_CUDA(cudaEventCreate(&a));
+    SR_CUDA(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms up
+        SR_CUDA(cudaEventRecord(a, e->stream));
+        if (variant == 0) fp32_pipe_kernel<0><<<grid, 256, 0, e->stream>>>(d_out, iters, 1e-9f);
+        else if (variant == 1) fp32_pipe_kernel<1><<<grid, 256, 0, e->stream>>>(d_out, iters, 1e-9f);
+        else fp32_pipe_kernel<2><<<grid, 256, 0, e->stream>>>(d_out, iters, 1e-9f);
+        SR_CUDA(cudaGetLastError());
+        SR_CUDA(cudaEventRecord(b, e->stream));
+        SR_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        SR_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+        ++e->launches;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_out);
+    // one "step" = 8 accumulators x 12 FMA-equivalents x 2 flop
+    *tflops = (double)grid * 256.0 * iters * 12.0 * 8.0 * 2.0 / (best * 1e-3) / 1e12;
+    return SR_OK;
+}
+
+int sr_engine_synchronize(sr_engine *e)
+{
+    if (!e) return SR_EINVAL;
+    SR_CUDA(cudaSetDevice(e->device));
+    SR_CUDA(cudaStreamSynchronize(e->stream));
+    return SR_OK;
+}
+
+}  // extern "C"

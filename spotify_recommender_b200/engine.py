@@ -1,0 +1,208 @@
+"""Python binding of the C ABI (include/sr_engine.h) -- ctypes only, no torch types in
+the signatures.  This module is the host-side mirror of the reference's scoring API
+(`Recommender::recommendByIndex`, Recommender.cu:275-318) for whole query batches.
+
+There is NO CPU fallback: if libsr_engine.so is missing or no sm_100 device is
+present, construction raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ENGINE_SO = os.path.join(PKG, "libsr_engine.so")
+FEATURE_COUNT = 12  # reference Song.h:12
+
+SR_OK, SR_EINVAL, SR_ENODEVICE, SR_ECUDA, SR_ENOMEM, SR_ESTATE = range(6)
+_ERRNAMES = {1: "SR_EINVAL", 2: "SR_ENODEVICE", 3: "SR_ECUDA", 4: "SR_ENOMEM", 5: "SR_ESTATE"}
+
+EXPORTS = [
+    "sr_engine_create", "sr_engine_destroy", "sr_engine_last_error", "sr_engine_load_features",
+    "sr_engine_load_features_device", "sr_engine_song_count", "sr_engine_query_by_index",
+    "sr_engine_query_by_vector", "sr_engine_query_by_index_dev", "sr_engine_query_by_vector_dev",
+    "sr_engine_merge_topk_dev", "sr_engine_all_pairs_topk", "sr_engine_set_option", "sr_engine_get_stat",
+    "sr_engine_get_timing", "sr_engine_variant_name", "sr_engine_measure_fp32", "sr_engine_synchronize",
+]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{_ERRNAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree engine; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(ENGINE_SO):
+        raise FileNotFoundError(
+            f"{ENGINE_SO} is missing: build it with `python -m spotify_recommender_b200.build` "
+            "(the CUDA engine is the only implementation; there is no CPU fallback)")
+    L = C.CDLL(ENGINE_SO)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.sr_engine_create.argtypes = [C.POINTER(vp), i32]
+    L.sr_engine_destroy.argtypes = [vp]
+    L.sr_engine_destroy.restype = None
+    L.sr_engine_last_error.argtypes = [vp]
+    L.sr_engine_last_error.restype = C.c_char_p
+    L.sr_engine_load_features.argtypes = [vp, vp, i64, i64]
+    L.sr_engine_load_features_device.argtypes = [vp, vp, i64, i64]
+    L.sr_engine_song_count.argtypes = [vp]
+    L.sr_engine_song_count.restype = i64
+    L.sr_engine_query_by_index.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.sr_engine_query_by_vector.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    L.sr_engine_query_by_index_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.sr_engine_query_by_vector_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.sr_engine_merge_topk_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    L.sr_engine_all_pairs_topk.argtypes = [vp, i64, i64, i32, vp, vp]
+    L.sr_engine_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.sr_engine_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
+    L.sr_engine_get_timing.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.sr_engine_variant_name.argtypes = [i32]
+    L.sr_engine_variant_name.restype = C.c_char_p
+    L.sr_engine_measure_fp32.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    L.sr_engine_synchronize.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def variant_names() -> list[str]:
+    L = load_library()
+    out, i = [], 0
+    while True:
+        n = L.sr_engine_variant_name(i)
+        if n is None:
+            return out
+        out.append(n.decode())
+        i += 1
+
+
+def _ptr(a) -> C.c_void_p:
+    """numpy array -> host pointer; torch CUDA tensor / int -> device pointer."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+class Engine:
+    """One scoring engine = one CUDA device (one process per GPU in multi-GPU runs)."""
+
+    def __init__(self, device: int = -1):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.sr_engine_create(C.byref(h), device)
+        if rc != SR_OK:
+            raise EngineError(rc, self.L.sr_engine_last_error(None).decode())
+        self.h = h
+
+    # -- lifecycle -----------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.L.sr_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != SR_OK:
+            raise EngineError(rc, self.L.sr_engine_last_error(self.h).decode())
+
+    # -- store (replaces Recommender::initialize, Recommender.cu:100-182) -------
+    def load_features(self, rows, id_base: int = 0) -> None:
+        """rows: host float32 (n, 12) array, or a torch CUDA tensor of that shape."""
+        if isinstance(rows, np.ndarray):
+            rows = np.ascontiguousarray(rows, np.float32)
+            if rows.ndim != 2 or rows.shape[1] != FEATURE_COUNT:
+                raise ValueError("rows must be (n, 12) float32")
+            self._check(self.L.sr_engine_load_features(self.h, _ptr(rows), rows.shape[0], id_base))
+        else:
+            if tuple(rows.shape[1:]) != (FEATURE_COUNT,) or not rows.is_contiguous():
+                raise ValueError("rows must be a contiguous (n, 12) float32 CUDA tensor")
+            self._check(self.L.sr_engine_load_features_device(self.h, _ptr(rows), rows.shape[0], id_base))
+
+    @property
+    def song_count(self) -> int:
+        return int(self.L.sr_engine_song_count(self.h))
+
+    # -- queries, HOST buffers (the public, end-to-end path) -------------------
+    def query_by_index(self, qidx, k: int, scores: bool = True):
+        """Batch form of Recommender::recommendByIndex (Recommender.cu:275-318):
+        each query song excludes itself; returns (idx[nq,k] int32, score[nq,k] f32)."""
+        qidx = np.ascontiguousarray(qidx, np.int32).ravel()
+        out_i = np.empty((qidx.size, max(k, 0)), np.int32)
+        out_s = np.empty((qidx.size, max(k, 0)), np.float32) if scores else None
+        self._check(self.L.sr_engine_query_by_index(self.h, _ptr(qidx), qidx.size, k, _ptr(out_i), _ptr(out_s)))
+        return out_i, out_s
+
+    def query_by_vector(self, qrows, k: int, exclude=None, scores: bool = True):
+        qrows = np.ascontiguousarray(qrows, np.float32).reshape(-1, FEATURE_COUNT)
+        ex = None if exclude is None else np.ascontiguousarray(exclude, np.int32).ravel()
+        out_i = np.empty((qrows.shape[0], max(k, 0)), np.int32)
+        out_s = np.empty((qrows.shape[0], max(k, 0)), np.float32) if scores else None
+        self._check(self.L.sr_engine_query_by_vector(self.h, _ptr(qrows), _ptr(ex), qrows.shape[0], k,
+                                                     _ptr(out_i), _ptr(out_s)))
+        return out_i, out_s
+
+    def all_pairs_topk(self, q_lo: int, q_hi: int, k: int, scores: bool = True):
+        out_i = np.empty((q_hi - q_lo, k), np.int32)
+        out_s = np.empty((q_hi - q_lo, k), np.float32) if scores else None
+        self._check(self.L.sr_engine_all_pairs_topk(self.h, q_lo, q_hi, k, _ptr(out_i), _ptr(out_s)))
+        return out_i, out_s
+
+    # -- queries, DEVICE buffers (stream-ordered, not synchronised) ------------
+    def query_by_index_dev(self, d_qidx, nq: int, k: int, d_out_idx, d_out_score=None, stream: int = 0) -> None:
+        self._check(self.L.sr_engine_query_by_index_dev(self.h, _ptr(d_qidx), nq, k, _ptr(d_out_idx),
+                                                        _ptr(d_out_score), C.c_void_p(stream)))
+
+    def query_by_vector_dev(self, d_qrows, d_exclude, nq: int, k: int, d_out_idx, d_out_score=None,
+                            stream: int = 0) -> None:
+        self._check(self.L.sr_engine_query_by_vector_dev(self.h, _ptr(d_qrows), _ptr(d_exclude), nq, k,
+                                                         _ptr(d_out_idx), _ptr(d_out_score), C.c_void_p(stream)))
+
+    def merge_topk_dev(self, d_idx, d_score, parts: int, nq: int, k: int, d_out_idx, d_out_score=None,
+                       stream: int = 0) -> None:
+        self._check(self.L.sr_engine_merge_topk_dev(self.h, _ptr(d_idx), _ptr(d_score), parts, nq, k,
+                                                    _ptr(d_out_idx), _ptr(d_out_score), C.c_void_p(stream)))
+
+    # -- knobs / introspection -----------------------------------------------
+    def set_option(self, key: str, value: int) -> None:
+        self._check(self.L.sr_engine_set_option(self.h, key.encode(), int(value)))
+
+    def stat(self, key: str) -> int:
+        v = C.c_int64()
+        self._check(self.L.sr_engine_get_stat(self.h, key.encode(), C.byref(v)))
+        return int(v.value)
+
+    def timing(self, kernel: str):
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self.L.sr_engine_get_timing(self.h, kernel.encode(), C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def measure_fp32(self, variant: int = 1) -> float:
+        t = C.c_double()
+        self._check(self.L.sr_engine_measure_fp32(self.h, variant, C.byref(t)))
+        return float(t.value)
+
+    def synchronize(self) -> None:
+        self._check(self.L.sr_engine_synchronize(self.h))
