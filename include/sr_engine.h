@@ -131,6 +131,11 @@ const char *sr_engine_variant_name(int i);
  * FMUL+FADD (the oracle's instruction mix).  Returns TFLOP/s (2 flop per FMA). */
 int sr_engine_measure_fp32(sr_engine *e, int variant, double *tflops);
 
+/* Self-test hook: out[i] = the engine's device-side IEEE division a[i] / b[i] (b > 0),
+ * the one operation of the reference's scoring (Recommender.cu:271) that is not a
+ * single hardware instruction on the GPU.  HOST buffers.  Used by the tests only. */
+int sr_engine_selftest_div(sr_engine *e, const float *a, const float *b, int n, float *out);
+
 /* Blocks until everything enqueued on the engine's own stream has finished. */
 int sr_engine_synchronize(sr_engine *e);
 

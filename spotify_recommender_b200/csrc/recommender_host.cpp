@@ -1,0 +1,246 @@
+// recommender_host.cpp -- the C++ host class of include/sr_recommender.hpp on top of
+// the C ABI (include/sr_engine.h), plus a small C API around it for FFI users and tests.
+// Mirrors the reference's operator interface for the hot path: same names, argument
+// meaning and error behaviour (messages on std::cerr, empty vector / false on failure;
+// reference Recommender.cu:100-107, :276-284, :356-372).
+#include "sr_recommender.hpp"
+
+#include <algorithm>
+#include <cctype>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <unordered_map>
+
+#include "sr_engine.h"
+
+struct Recommender::Impl {
+    sr_engine *engine = nullptr;
+    // query resolution indexes: first occurrence wins, as the reference's
+    // linear scans return the first match (Recommender.cu:320-327, :336-354)
+    std::unordered_map<std::string, int> by_id;
+    std::unordered_map<std::string, int> by_lower_name;
+    std::string lower_blob;            // all lower-cased names, '\0'-separated
+    std::vector<uint32_t> lower_off;   // start of name i in lower_blob (size n+1)
+};
+
+namespace {
+std::string lower(const std::string &s)
+{
+    std::string r = s;
+    std::transform(r.begin(), r.end(), r.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    return r;
+}
+}  // namespace
+
+Recommender::Recommender() : initialized(false), numSongs(0), gpuEnabled(false), impl(new Impl()) {}
+
+Recommender::~Recommender()
+{
+    if (impl) {
+        if (impl->engine) sr_engine_destroy(impl->engine);
+        delete impl;
+    }
+}
+
+bool Recommender::initializeDense(const float *features, long long count)
+{
+    if (!features || count <= 0) {
+        std::cerr << "Error: Cannot initialize with empty song database" << std::endl;
+        return false;
+    }
+    if (count > 0x7fffffffLL) {
+        std::cerr << "Error: too many songs for 32-bit song indices: " << count << std::endl;
+        return false;
+    }
+    if (!impl->engine) {
+        if (sr_engine_create(&impl->engine, -1) != SR_OK) {
+            std::cerr << "Error: GPU engine unavailable: " << sr_engine_last_error(nullptr)
+                      << " (no CPU fallback in this build)" << std::endl;
+            impl->engine = nullptr;
+            return false;
+        }
+    }
+    if (sr_engine_load_features(impl->engine, features, count, 0) != SR_OK) {
+        std::cerr << "Error: failed to upload features: " << sr_engine_last_error(impl->engine) << std::endl;
+        return false;
+    }
+    numSongs = (int)count;
+    initialized = true;
+    gpuEnabled = true;
+    return true;
+}
+
+bool Recommender::initialize(const std::vector<Song> &songs)
+{
+    std::cout << "Initializing recommender (B200 engine)..." << std::endl;
+    if (songs.empty()) {
+        std::cerr << "Error: Cannot initialize with empty song database" << std::endl;
+        return false;
+    }
+    initialized = false;
+    gpuEnabled = false;
+    const size_t n = songs.size();
+    // AoS -> dense row-major n x 12 (what Recommender.cu:162-166 packs), then one upload
+    std::vector<float> dense(n * FEATURE_COUNT);
+    for (size_t i = 0; i < n; ++i) std::memcpy(&dense[i * FEATURE_COUNT], songs[i].features, sizeof(float) * FEATURE_COUNT);
+    impl->by_id.clear();
+    impl->by_lower_name.clear();
+    impl->lower_blob.clear();
+    impl->lower_off.assign(1, 0u);
+    impl->by_id.reserve(n * 2);
+    impl->by_lower_name.reserve(n * 2);
+    for (size_t i = 0; i < n; ++i) {
+        impl->by_id.emplace(songs[i].track_id, (int)i);  // emplace keeps the first
+        std::string l = lower(songs[i].track_name);
+        impl->by_lower_name.emplace(l, (int)i);
+        impl->lower_blob.append(l);
+        impl->lower_blob.push_back('\0');
+        impl->lower_off.push_back((uint32_t)impl->lower_blob.size());
+    }
+    if (!initializeDense(dense.data(), (long long)n)) return false;
+    std::cout << "Recommender initialized on GPU: " << numSongs << " songs resident" << std::endl;
+    return true;
+}
+
+std::vector<std::vector<Recommendation> > Recommender::recommendBatch(const std::vector<int> &idx, int topN)
+{
+    std::vector<std::vector<Recommendation> > out;
+    if (!initialized) {
+        std::cerr << "Error: Recommender not initialized" << std::endl;
+        return out;
+    }
+    if (topN <= 0 || idx.empty()) return out;
+    for (int q : idx) {
+        if (q < 0 || q >= numSongs) {
+            std::cerr << "Error: Invalid song index: " << q << std::endl;
+            return out;
+        }
+    }
+    const int k = std::min(topN, 1024);
+    std::vector<int32_t> qi(idx.begin(), idx.end());
+    std::vector<int32_t> oi(qi.size() * (size_t)k);
+    std::vector<float> os(qi.size() * (size_t)k);
+    if (sr_engine_query_by_index(impl->engine, qi.data(), (int)qi.size(), k, oi.data(), os.data()) != SR_OK) {
+        std::cerr << "Error: GPU query failed: " << sr_engine_last_error(impl->engine) << std::endl;
+        return out;
+    }
+    out.resize(qi.size());
+    for (size_t q = 0; q < qi.size(); ++q)
+        for (int r = 0; r < k && oi[q * k + r] >= 0; ++r) out[q].emplace_back(oi[q * k + r], os[q * k + r]);
+    return out;
+}
+
+std::vector<int> Recommender::recommendByIndex(int songIndex, int topN)
+{
+    if (!initialized) {
+        std::cerr << "Error: Recommender not initialized" << std::endl;
+        return {};
+    }
+    if (songIndex < 0 || songIndex >= numSongs) {
+        std::cerr << "Error: Invalid song index: " << songIndex << std::endl;
+        return {};
+    }
+    std::vector<int> res;
+    std::vector<std::vector<Recommendation> > b = recommendBatch(std::vector<int>(1, songIndex), topN);
+    if (b.empty()) return res;
+    res.reserve(b[0].size());
+    for (const Recommendation &r : b[0]) res.push_back(r.songIndex);
+    return res;
+}
+
+int Recommender::findSongByTrackId(const std::string &trackId) const
+{
+    auto it = impl->by_id.find(trackId);
+    return it == impl->by_id.end() ? -1 : it->second;
+}
+
+int Recommender::findSongByName(const std::string &trackName) const
+{
+    const std::string q = lower(trackName);
+    auto it = impl->by_lower_name.find(q);  // first case-insensitive exact match
+    if (it != impl->by_lower_name.end()) return it->second;
+    // else the first song whose lower-cased name contains the query
+    const std::string &blob = impl->lower_blob;
+    const size_t n = impl->lower_off.size() - 1;
+    if (q.empty()) return n ? 0 : -1;
+    if (q.find('\0') != std::string::npos) return -1;
+    size_t pos = blob.find(q);
+    if (pos == std::string::npos) return -1;
+    // names are '\0'-separated and q has no '\0', so a hit lies inside one name
+    size_t i = std::upper_bound(impl->lower_off.begin(), impl->lower_off.end(), (uint32_t)pos) - impl->lower_off.begin() - 1;
+    return i < n ? (int)i : -1;
+}
+
+std::vector<int> Recommender::recommend(const std::string &trackId, int topN)
+{
+    int index = findSongByTrackId(trackId);
+    if (index == -1) {
+        std::cerr << "Error: Song with track_id '" << trackId << "' not found" << std::endl;
+        return {};
+    }
+    return recommendByIndex(index, topN);
+}
+
+std::vector<int> Recommender::recommendByName(const std::string &trackName, int topN)
+{
+    int index = findSongByName(trackName);
+    if (index == -1) {
+        std::cerr << "Error: Song with name '" << trackName << "' not found" << std::endl;
+        return {};
+    }
+    return recommendByIndex(index, topN);
+}
+
+// ---- C API around the class (FFI users, tests) -------------------------------------------
+extern "C" {
+
+// ids / names may be NULL: songs are then called "id<i>" / "Track <i>".
+void *sr_recommender_create(const float *features, int64_t n, const char *const *ids, const char *const *names)
+{
+    if (!features || n <= 0) return nullptr;
+    std::vector<Song> songs((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        Song &s = songs[(size_t)i];
+        s.track_id = ids ? ids[i] : "id" + std::to_string(i);
+        s.track_name = names ? names[i] : "Track " + std::to_string(i);
+        s.artists = "Artist";
+        s.genre_id = 0;
+        std::memcpy(s.features, features + i * FEATURE_COUNT, sizeof(s.features));
+    }
+    Recommender *r = new Recommender();
+    std::streambuf *old = std::cout.rdbuf(nullptr);
+    const bool ok = r->initialize(songs);
+    std::cout.rdbuf(old);
+    if (!ok) {
+        delete r;
+        return nullptr;
+    }
+    return r;
+}
+
+void sr_recommender_destroy(void *h) { delete static_cast<Recommender *>(h); }
+int sr_recommender_song_count(void *h) { return static_cast<Recommender *>(h)->getSongCount(); }
+int sr_recommender_gpu_enabled(void *h) { return static_cast<Recommender *>(h)->isGPUEnabled() ? 1 : 0; }
+
+static int copy_out(const std::vector<int> &r, int32_t *out)
+{
+    for (size_t i = 0; i < r.size(); ++i) out[i] = r[i];
+    return (int)r.size();
+}
+int sr_recommender_by_index(void *h, int idx, int k, int32_t *out)
+{
+    return copy_out(static_cast<Recommender *>(h)->recommendByIndex(idx, k), out);
+}
+int sr_recommender_by_name(void *h, const char *name, int k, int32_t *out)
+{
+    return copy_out(static_cast<Recommender *>(h)->recommendByName(name, k), out);
+}
+int sr_recommender_by_id(void *h, const char *id, int k, int32_t *out)
+{
+    return copy_out(static_cast<Recommender *>(h)->recommend(id, k), out);
+}
+int sr_recommender_find_name(void *h, const char *name) { return static_cast<Recommender *>(h)->findSongByName(name); }
+int sr_recommender_find_id(void *h, const char *id) { return static_cast<Recommender *>(h)->findSongByTrackId(id); }
+
+}  // extern "C"

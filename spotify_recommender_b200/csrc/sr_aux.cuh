@@ -3,6 +3,7 @@
 // FP32 pipe microbenchmark used as the measured roofline denominator.
 #pragma once
 #include "sr_device.cuh"
+#include "sr_scan.cuh"
 
 namespace sr {
 
@@ -12,15 +13,17 @@ namespace sr {
 // hat  : row / ||row|| computed in double and rounded once; +NaN for irregular rows
 //        (norm not 0 and outside [kNormLo,kNormHi], or not finite): those always pass
 //        the scan filter and are therefore always scored exactly.
-__global__ void build_store_kernel(const float *raw, int64_t n, int64_t n_pad, float *nf, float *hat,
+//        laid out for the scan kernel shape (S, THREADS): see hat_offset() in sr_scan.cuh
+__global__ void build_store_kernel(const float *raw, int64_t n, int64_t n_pad, float *nf, float *hat, int S, int THREADS,
                                    unsigned long long *n_irregular)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
-    float4 *hp = reinterpret_cast<float4 *>(hat) + i * 3;
+    float *hp = hat + hat_offset(i, 0, S, THREADS);  // feature j lives at hp[2 * j]
     if (i >= n) {
         nf[i] = 0.0f;
-        hp[0] = hp[1] = hp[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kF; ++j) hp[2 * j] = 0.0f;
         return;
     }
     float f[kF];
@@ -44,9 +47,8 @@ __global__ void build_store_kernel(const float *raw, int64_t n, int64_t n_pad, f
         for (int j = 0; j < kF; ++j) h[j] = qnan;
         atomicAdd(n_irregular, 1ull);
     }
-    hp[0] = make_float4(h[0], h[1], h[2], h[3]);
-    hp[1] = make_float4(h[4], h[5], h[6], h[7]);
-    hp[2] = make_float4(h[8], h[9], h[10], h[11]);
+#pragma unroll
+    for (int j = 0; j < kF; ++j) hp[2 * j] = h[j];
 }
 
 // ---- query preparation -------------------------------------------------------
@@ -63,7 +65,8 @@ struct PrepArgs {
     int nq;
     float *qraw, *qn, *qhat;  // outputs
     int32_t *excl;
-    int32_t *pool_cnt;
+    int32_t *gcnt, *glock;    // per-query list state, reset here
+    uint64_t *gmin;
     uint32_t *g_best;
     int32_t *bad_index;       // set to 1 when a gather id is not owned by this store
 };
@@ -107,7 +110,9 @@ __global__ void prep_queries_kernel(const PrepArgs a)
         // pair passes the filter and is scored exactly
         a.qhat[(size_t)q * kF + j] = regular ? (float)((double)v[j] * inv) : qnan;
     }
-    a.pool_cnt[q] = 0;
+    a.gcnt[q] = 0;
+    a.glock[q] = 0;
+    a.gmin[q] = 0ull;
     a.g_best[q] = kOrdNegInf;
 }
 
@@ -186,11 +191,11 @@ __device__ __forceinline__ int block_select_topk(uint64_t *s_keys, int total, in
     return valid;
 }
 
-// One CTA per query: the exact survivors of every scan segment -> ordered top-K.
+// One CTA per query: the scan's exact (unordered) top-K list -> ordered output rows.
 struct FinalArgs {
-    const uint64_t *pool;
-    const int32_t *pool_cnt;
-    int nq, K, segs;
+    const uint64_t *glist;
+    const int32_t *gcnt;
+    int nq, K;
     int32_t *out_idx;    // [nq][K]
     float *out_score;    // [nq][K] or null
 };
@@ -201,8 +206,8 @@ __global__ void __launch_bounds__(THREADS) finalize_kernel(const FinalArgs a)
     __shared__ uint64_t s_keys[kSortCap];
     const int q = blockIdx.x;
     if (q >= a.nq) return;
-    const uint64_t *slab = a.pool + (size_t)q * a.segs * a.K;
-    const int P = a.pool_cnt[q];
+    const uint64_t *slab = a.glist + (size_t)q * a.K;
+    const int P = min(a.gcnt[q], a.K);
     int valid = 0;
     if (P > 0) valid = block_select_topk<THREADS>(s_keys, P, a.K, [&](int i) { return slab[i]; });
     for (int r = threadIdx.x; r < a.K; r += THREADS) {
@@ -234,6 +239,13 @@ __global__ void __launch_bounds__(THREADS) merge_parts_kernel(const int32_t *idx
         out_idx[(size_t)q * K + r] = ok ? (int32_t)key_id(k) : -1;
         if (out_score) out_score[(size_t)q * K + r] = ok ? key_score(k) : 0.0f;
     }
+}
+
+// ---- self-test hook: the engine's division, element-wise (tests only) ----------------
+__global__ void div_selftest_kernel(const float *a, const float *b, float *out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ieee_div_pos(a[i], b[i]);
 }
 
 // ---- FP32 pipe microbenchmark ----------------------------------------------

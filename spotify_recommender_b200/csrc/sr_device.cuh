@@ -69,12 +69,41 @@ __device__ __forceinline__ float exact_norm(const float *f)
     return __fsqrt_rn(acc);
 }
 
+// IEEE-754 round-to-nearest FP32 division a / b for b > 0, WITHOUT the subroutine call
+// nvcc emits for `/` and __fdiv_rn (its slow path is a CALL, and one CALL anywhere in a
+// kernel makes ptxas stop keeping warp-uniform operands in uniform registers -- which is
+// what the scan's FFMA2 stream lives on).  The quotient is formed in double precision
+// from MUFU.RCP64H + two Newton steps + one residual correction (relative error < 2^-51)
+// and rounded once to FP32.  That equals the correctly rounded FP32 quotient: the exact
+// quotient of two 24-bit significands is never closer than 2^-49 (relative) to a rounding
+// boundary of the 24-bit (or a subnormal) format, so the double result always rounds the
+// same way.  tests/test_engine_gpu.py::test_division_matches_ieee pins it against the
+// host's divss bit for bit.
+__device__ __forceinline__ float ieee_div_pos(float a, float b)
+{
+    if (!(fabsf(a) <= 3.402823466e+38f) || !(b <= 3.402823466e+38f)) {
+        // a is NaN/inf or b is +inf/NaN: finite/inf = signed 0, everything else NaN or inf
+        if (a != a || b != b) return __int_as_float(0x7fc00000);
+        if (fabsf(a) > 3.402823466e+38f) return (b > 3.402823466e+38f) ? __int_as_float(0x7fc00000) : a;
+        return copysignf(0.0f, a);
+    }
+    if (a == 0.0f) return a;  // keeps the sign of a zero numerator
+    const double bd = (double)b, ad = (double)a;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(bd));
+    r = fma(r, fma(-bd, r, 1.0), r);
+    r = fma(r, fma(-bd, r, 1.0), r);
+    double q = ad * r;
+    q = fma(fma(-bd, q, ad), r, q);
+    return __double2float_rn(q);
+}
+
 __device__ __forceinline__ float exact_finish(float dot, float nf, float qn)
 {
     float den = __fmul_rn(nf, qn);
     float s = 0.0f;
     if (den > 1e-8f) {
-        s = __fdiv_rn(dot, den);
+        s = ieee_div_pos(dot, den);
         s = (s < 1.0f) ? s : 1.0f;     // std::min(1.0f, s)
         s = (-1.0f < s) ? s : -1.0f;   // std::max(-1.0f, s)
     }

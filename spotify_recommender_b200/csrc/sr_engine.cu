@@ -85,16 +85,18 @@ struct sr_engine {
     int64_t n = 0, n_pad = 0;
     int32_t id_base = 0;
     int64_t irregular = 0;
+    int hat_variant = -1;  // kernel shape d_hat is laid out for
 
     // options
     int variant = 0;
     int qt_opt = kQTMax;
     int batch = 8192;
     int sample = -1;  // -1: automatic
+    int hit_cap = 128; // hit-buffer entries per query in shared memory
     bool profile = false;
 
     // batch workspace (grow-only)
-    DevBuf qraw, qn, qhat, excl, gbest, pool_cnt, pool, cta_buf, out_idx, out_score, qin, exin;
+    DevBuf qraw, qn, qhat, excl, gbest, gcnt, glock, gmin, glist, out_idx, out_score, qin, exin;
     unsigned long long *d_stats = nullptr;  // [8]
     unsigned long long *d_irregular = nullptr;
     int32_t *d_flag = nullptr;
@@ -216,7 +218,9 @@ int build_store(sr_engine *e)
     const int threads = 256;
     const int64_t blocks = (e->n_pad + threads - 1) / threads;
     build_store_kernel<<<(unsigned)blocks, threads, 0, e->stream>>>(e->d_raw, e->n, e->n_pad, e->d_nf, e->d_hat,
+                                                                     kVariants[e->variant].S, kVariants[e->variant].threads,
                                                                      e->d_irregular);
+    e->hat_variant = e->variant;
     SR_CUDA(cudaGetLastError());
     ++e->launches;
     unsigned long long irr = 0;
@@ -263,7 +267,6 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
 {
     const Variant &v = kVariants[e->variant];
     const int TS = v.S * v.threads;
-    const int warps = v.threads / 32;
     const int n_tiles = (int)((e->n + TS - 1) / TS);
     // query groups (what fits the constant bank), evenly filled; then query tiles inside a group
     const int groups = (nq + kConstQueries - 1) / kConstQueries;
@@ -272,16 +275,15 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     const int nqt0 = (gsize + qt_cap - 1) / qt_cap;
     const int qt = (gsize + nqt0 - 1) / nqt0;
     const int nqt = (gsize + qt - 1) / qt;
-    const size_t smem = scan_smem_bytes(qt, warps);
+    const int cap = e->hit_cap;
+    const size_t smem = scan_smem_bytes(qt, cap);
     int ctas = 0;
     SR_CUDA(v.occ(&ctas, smem));
     if (ctas < 1) return fail(e, SR_ECUDA, "scan kernel %s does not fit one SM (smem %zu)", v.name, smem);
     const int64_t units = (int64_t)nqt * n_tiles;
+    if (units > 0x7fffffffLL) return fail(e, SR_EINVAL, "store too large for one pass (%lld work units)", (long long)units);
     const int grid = (int)std::min<int64_t>((int64_t)e->sm_count * ctas, units);
     e->scan_grid = grid;
-    const int bufcap = (std::max(2 * K, K + 256) + 31) / 32 * 32;
-    const int prune_at = K + (bufcap - K) / 2;
-    const int segs = scan_segs(grid, nqt);
 
     int rc;
     if ((rc = ensure(e, e->qraw, (size_t)nq * kF * 4))) return rc;
@@ -289,24 +291,25 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->qhat, (size_t)nq * kF * 4))) return rc;
     if ((rc = ensure(e, e->excl, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gbest, (size_t)nq * 4))) return rc;
-    if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
-    if ((rc = ensure(e, e->pool, (size_t)nq * segs * K * 8))) return rc;
-    if ((rc = ensure(e, e->cta_buf, (size_t)grid * qt * bufcap * 8))) return rc;
+    if ((rc = ensure(e, e->gcnt, (size_t)nq * 4))) return rc;
+    if ((rc = ensure(e, e->glock, (size_t)nq * 4))) return rc;
+    if ((rc = ensure(e, e->gmin, (size_t)nq * 8))) return rc;
+    if ((rc = ensure(e, e->glist, (size_t)nq * K * 8))) return rc;
 
     {
         PrepArgs p;
         p.raw_store = e->d_raw; p.n = e->n; p.id_base = e->id_base;
         p.qidx = d_qidx; p.qrows_in = d_qrows; p.excl_in = d_excl; p.nq = nq;
         p.qraw = (float *)e->qraw.p; p.qn = (float *)e->qn.p; p.qhat = (float *)e->qhat.p;
-        p.excl = (int32_t *)e->excl.p; p.pool_cnt = (int32_t *)e->pool_cnt.p;
-        p.g_best = (uint32_t *)e->gbest.p; p.bad_index = e->d_flag;
+        p.excl = (int32_t *)e->excl.p; p.gcnt = (int32_t *)e->gcnt.p; p.glock = (int32_t *)e->glock.p;
+        p.gmin = (uint64_t *)e->gmin.p; p.g_best = (uint32_t *)e->gbest.p; p.bad_index = e->d_flag;
         Scope sc(e, st, kPrep);
         prep_queries_kernel<<<(nq + 127) / 128, 128, 0, st>>>(p);
         SR_CUDA(cudaGetLastError());
     }
     // threshold bootstrap
     int m = e->sample;
-    if (m < 0) m = std::min(kSortCap, std::max(1024, pow2_floor((int64_t)K * 32)));
+    if (m < 0) m = std::min(kSortCap, std::max(1024, 2 * pow2_floor((int64_t)K * 32 - 1)));
     if (m > 0) {
         m = std::min(m, pow2_floor(e->n / 4));  // only worth it on stores much larger than the sample
         if (m >= 2 * K && m >= 64) {
@@ -326,13 +329,16 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.n_tiles = n_tiles;
         a.qraw = (float *)e->qraw.p + (size_t)g0 * kF; a.qn = (float *)e->qn.p + g0;
         a.exclude = (int32_t *)e->excl.p + g0; a.nq = gq; a.qt = qt;
-        a.K = K; a.prune_at = prune_at; a.bufcap = bufcap;
-        a.cta_buf = (uint64_t *)e->cta_buf.p; a.g_best = (uint32_t *)e->gbest.p + g0;
-        a.pool = (uint64_t *)e->pool.p + (size_t)g0 * segs * K; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
-        a.segs = segs;
+        a.K = K; a.cap = cap; a.settle_at = std::max(1, cap / 4);
+        a.glist = (uint64_t *)e->glist.p + (size_t)g0 * K; a.gcnt = (int32_t *)e->gcnt.p + g0;
+        a.gmin = (uint64_t *)e->gmin.p + g0; a.glock = (int32_t *)e->glock.p + g0;
+        a.g_best = (uint32_t *)e->gbest.p + g0;
         a.stats = e->d_stats;
         const int gnqt = (gq + qt - 1) / qt;
-        const int ggrid = (int)std::min<int64_t>(grid, (int64_t)gnqt * n_tiles);
+        const int64_t gunits = (int64_t)gnqt * n_tiles;
+        const int ggrid = (int)std::min<int64_t>(grid, gunits);
+        a.upc = (int)(gunits / ggrid);
+        a.extra = (int)(gunits % ggrid);
         std::lock_guard<std::mutex> lock(g_bank_mutex);
         cudaEvent_t &ev = g_bank_event[e->device & 63];
         if (!ev) SR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -347,8 +353,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     }
     {
         FinalArgs f;
-        f.pool = (uint64_t *)e->pool.p; f.pool_cnt = (int32_t *)e->pool_cnt.p;
-        f.nq = nq; f.K = K; f.segs = segs; f.out_idx = d_out_idx; f.out_score = d_out_score;
+        f.glist = (uint64_t *)e->glist.p; f.gcnt = (int32_t *)e->gcnt.p;
+        f.nq = nq; f.K = K; f.out_idx = d_out_idx; f.out_score = d_out_score;
         Scope sc(e, st, kFinalize);
         finalize_kernel<256><<<nq, 256, 0, st>>>(f);
         SR_CUDA(cudaGetLastError());
@@ -466,8 +472,8 @@ void sr_engine_destroy(sr_engine *e)
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto &t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->pool_cnt, &e->pool,
-                      &e->cta_buf, &e->out_idx, &e->out_score, &e->qin, &e->exin};
+    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gcnt, &e->glock, &e->gmin,
+                      &e->glist, &e->out_idx, &e->out_score, &e->qin, &e->exin};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->d_raw) cudaFree(e->d_raw);
@@ -604,6 +610,12 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
     if (!strcmp(key, "variant")) {
         if (value < 0 || value >= kNumVariants) return fail(e, SR_EINVAL, "variant must be in [0, %d)", kNumVariants);
         e->variant = (int)value;
+        if (e->d_raw && e->hat_variant != e->variant) {  // the normalised store is laid out per kernel shape
+            SR_CUDA(cudaSetDevice(e->device));
+            SR_CUDA(cudaStreamSynchronize(e->stream));
+            int rc = build_store(e);
+            if (rc) return rc;
+        }
     } else if (!strcmp(key, "qt")) {
         if (value < 1 || value > kQTMax) return fail(e, SR_EINVAL, "qt must be in [1, %d]", kQTMax);
         e->qt_opt = (int)value;
@@ -614,6 +626,9 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
         if (value > kSortCap || (value > 0 && (value & (value - 1))))
             return fail(e, SR_EINVAL, "sample must be 0, negative (auto) or a power of two <= %d", kSortCap);
         e->sample = (int)value;
+    } else if (!strcmp(key, "hit_cap")) {
+        if (value < 32 || value > 1024 || value % 32) return fail(e, SR_EINVAL, "hit_cap must be a multiple of 32 in [32, 1024]");
+        e->hit_cap = (int)value;
     } else if (!strcmp(key, "profile")) {
         e->profile = value != 0;
     } else if (!strcmp(key, "reset")) {
@@ -634,8 +649,8 @@ int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value)
 {
     if (!e || !key || !value) return SR_EINVAL;
     SR_CUDA(cudaSetDevice(e->device));
-    static const char *const dev_keys[] = {"filter_hits", "settles", "rescans", "rescored"};
-    for (int i = 0; i < 4; ++i) {
+    static const char *const dev_keys[] = {"filter_hits", "settles", "rescans", "rescored", "inserts"};
+    for (int i = 0; i < 5; ++i) {
         if (!strcmp(key, dev_keys[i])) {
             unsigned long long h[8];
             SR_CUDA(cudaStreamSynchronize(e->stream));
@@ -705,6 +720,22 @@ int sr_engine_measure_fp32(sr_engine *e, int variant, double *tflops)
     cudaFree(d_out);
     // one "step" = 8 accumulators x 12 FMA-equivalents x 2 flop
     *tflops = (double)grid * 256.0 * iters * 12.0 * 8.0 * 2.0 / (best * 1e-3) / 1e12;
+    return SR_OK;
+}
+
+int sr_engine_selftest_div(sr_engine *e, const float *a, const float *b, int n, float *out)
+{
+    if (!e || !a || !b || !out || n <= 0) return SR_EINVAL;
+    SR_CUDA(cudaSetDevice(e->device));
+    float *d = nullptr;
+    SR_CUDA(cudaMalloc(&d, (size_t)n * 12));
+    SR_CUDA(cudaMemcpy(d, a, (size_t)n * 4, cudaMemcpyHostToDevice));
+    SR_CUDA(cudaMemcpy(d + n, b, (size_t)n * 4, cudaMemcpyHostToDevice));
+    div_selftest_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(d, d + n, d + 2 * (size_t)n, n);
+    SR_CUDA(cudaGetLastError());
+    SR_CUDA(cudaStreamSynchronize(e->stream));
+    SR_CUDA(cudaMemcpy(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return SR_OK;
 }
 

@@ -37,37 +37,40 @@ constexpr int kConstQueries = 1280;
 __constant__ float4 c_qhat[kConstQueries * 3];
 
 struct ScanArgs {
-    const float *hat;        // normalised rows, n_pad x 12 (pad rows 0, irregular rows NaN)
+    const float *hat;        // normalised rows in the kernel shape's pair-interleaved tile layout
+                             // (hat_offset(); pad rows 0, irregular rows NaN)
     const float *raw;        // raw rows, n_pad x 12
     const float *nf;         // exact row norms (reference order), n_pad
     int64_t n;               // valid local rows
     int32_t id_base;         // global id of local row 0
     int n_tiles;             // ceil(n / TS)
+    int upc, extra;          // work units per CTA: CTA b owns upc + (b < extra) units, in order
     const float *qraw;       // [nq][12] raw query rows            (all per-query arrays are
     const float *qn;         // [nq] exact query norms               already offset to the first
     const int32_t *exclude;  // [nq] global id to skip or -1         query of this group)
     int nq;                  // queries in this group (<= kConstQueries), rows of c_qhat
     int qt;                  // queries per tile (<= kQTMax)
-    int K, prune_at, bufcap;
-    uint64_t *cta_buf;       // [grid][qt][bufcap] candidate buffers (L2 resident)
-    uint32_t *g_best;        // [nq] orderable exact K-th best score seen so far by anyone
-    uint64_t *pool;          // [nq][segs*K] exact keys handed to finalize
-    int32_t *pool_cnt;       // [nq]
-    int segs;
-    unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored
+    int K;
+    int cap;                 // hit-buffer entries per query (shared memory)
+    int settle_at;           // settle a query's hit buffer once it holds this many
+    // global per-query exact top-K state, shared by every CTA (lock-protected)
+    uint64_t *glist;         // [nq][K] exact keys, unordered
+    int32_t *gcnt;           // [nq] valid keys in glist
+    uint64_t *gmin;          // [nq] smallest key of a FULL list (the exact K-th best), else 0
+    int32_t *glock;          // [nq] 0 free / 1 held
+    uint32_t *g_best;        // [nq] orderable score: best known lower bound of the final K-th best
+    unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] inserts
 };
 
-__host__ __device__ inline size_t scan_smem_bytes(int qt, int warps)
+__host__ __device__ inline size_t scan_smem_bytes(int qt, int cap)
 {
-    return (size_t)qt * (kF + 6) * 4 + (size_t)warps * 256 * 4;
+    return (size_t)qt * (kF + 6 + cap) * 4;
 }
 
-__host__ __device__ inline int scan_segs(int grid, int nqt) { return (grid + nqt - 1) / nqt + 2; }
-
-// -T' for the filter record; never +-0 (a -0 accumulator would read as "below").
+// -T' for the filter; never +-0 (a -0 accumulator would read as "below").
 __device__ __forceinline__ float neg_threshold(uint32_t best_ord)
 {
-    float t = ord2f(best_ord) - kEps;  // -inf stays -inf => +inf record => everything passes
+    float t = ord2f(best_ord) - kEps;  // -inf stays -inf => +inf => everything passes
     float nt = -t;
     return (nt == 0.0f) ? 1.0e-30f : nt;
 }
@@ -76,6 +79,7 @@ struct QueryCtx {  // shared-memory views of one query tile
     float *nthr, *qraw, *qn;
     uint32_t *best;
     int *cnt, *excl, *qid;
+    uint32_t *hit;  // [qt][cap] global ids that passed the filter, not yet scored
 };
 
 // exact key of one (query, row) pair, 0 when the row is the excluded song
@@ -88,105 +92,161 @@ __device__ __forceinline__ uint64_t exact_key(const ScanArgs &a, int64_t row, co
     return make_key(exact_score(f, __ldg(a.nf + row), q, qn), (uint32_t)gid);
 }
 
-// Keep the best K valid keys of buf[0,cnt) at the front (unordered).  Returns the
-// new count; *kth = K-th best key when K valid keys exist, else 0.
-__device__ __forceinline__ int warp_keep_topk(uint64_t *buf, int cnt, int K, uint32_t *hist, uint64_t *kth)
+// ---- the global per-query list ------------------------------------------------------
+__device__ __forceinline__ void list_lock(int32_t *lock)
 {
-    const int lane = threadIdx.x & 31;
-    uint64_t cut = 1ull;  // keep every valid key
-    if (cnt > K) {
-        int rank;
-        const uint32_t vK = warp_radix_select(
-            cnt, K, hist, [&](int i, uint32_t *w) { *w = (uint32_t)(__ldcg(buf + i) >> 32); return true; }, &rank);
-        if (vK != 0u) {  // at least K valid keys: break the tie group by id
-            int r2;
-            const uint32_t lo = warp_radix_select(
-                cnt, rank, hist,
-                [&](int i, uint32_t *w) {
-                    const uint64_t k = __ldcg(buf + i);
-                    *w = (uint32_t)k;
-                    return (uint32_t)(k >> 32) == vK;
-                },
-                &r2);
-            cut = ((uint64_t)vK << 32) | lo;
-        }
-    }
-    int newcnt = 0;
-    uint64_t mn = ~0ull;
-    for (int base = 0; base < cnt; base += 32) {
-        const int i = base + lane;
-        const uint64_t key = (i < cnt) ? __ldcg(buf + i) : 0ull;
-        const bool p = key >= cut;
-        const uint32_t b = __ballot_sync(0xffffffffu, p);
-        const int pos = newcnt + __popc(b & ((1u << lane) - 1u));
-        if (p) { __stcg(buf + pos, key); mn = key < mn ? key : mn; }
-        newcnt += __popc(b);
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const uint64_t o = __shfl_xor_sync(0xffffffffu, mn, off);
-        mn = o < mn ? o : mn;
+    if ((threadIdx.x & 31) == 0) {
+        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(100);
+        __threadfence();
     }
     __syncwarp();
-    *kth = (newcnt >= K) ? mn : 0ull;
-    return newcnt;
+}
+__device__ __forceinline__ void list_unlock(int32_t *lock)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        atomicExch(lock, 0);
+    }
+    __syncwarp();
 }
 
-// Settle one query's candidate buffer (whole warp): score unscored entries exactly,
-// keep the best K, on overflow re-scan tile rows [tile_lo, tile_hi) exactly.
-__device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c, uint64_t *buf, int ql, int64_t tile_lo,
-                                            int64_t tile_hi, uint32_t *hist)
+// Insert one exact key into query qg's list (whole warp, lock held).  Keeps the best K
+// keys; duplicates (a song met twice, e.g. after a tile re-scan) are ignored.
+__device__ __forceinline__ void list_insert_locked(const ScanArgs &a, int qg, uint64_t key)
+{
+    const int lane = threadIdx.x & 31;
+    uint64_t *list = a.glist + (size_t)qg * a.K;
+    const int n = __ldcg(a.gcnt + qg);
+    // per-lane two smallest keys (and where the smallest sits), plus duplicate detection
+    uint64_t m1 = ~0ull, m2 = ~0ull;
+    int p1 = -1;
+    bool dup = false;
+    for (int i = lane; i < n; i += 32) {
+        const uint64_t k = __ldcg(list + i);
+        dup |= (k == key);
+        if (k < m1) { m2 = m1; m1 = k; p1 = i; } else if (k < m2) { m2 = k; }
+    }
+    if (__any_sync(0xffffffffu, dup)) return;
+    if (n < a.K) {
+        if (lane == 0) {
+            __stcg(list + n, key);
+            __stcg(a.gcnt + qg, n + 1);
+        }
+        if (n + 1 < a.K) return;
+        // the list just became full: its minimum is the exact K-th best so far
+        uint64_t mn = m1 < key ? m1 : key;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const uint64_t o = __shfl_xor_sync(0xffffffffu, mn, off);
+            mn = o < mn ? o : mn;
+        }
+        if (lane == 0) {
+            __stcg(a.gmin + qg, mn);
+            atomicMax(a.g_best + qg, (uint32_t)(mn >> 32));
+        }
+        return;
+    }
+    // full list: the new key replaces the minimum if it beats it
+    uint64_t g1 = m1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, g1, off);
+        g1 = o < g1 ? o : g1;
+    }
+    if (key <= g1) return;
+    // second smallest overall: lanes that own the minimum offer their runner-up
+    uint64_t g2 = (m1 == g1) ? m2 : m1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, g2, off);
+        g2 = o < g2 ? o : g2;
+    }
+    const uint64_t newmin = key < g2 ? key : g2;
+    if (m1 == g1) __stcg(list + p1, key);  // keys are unique: exactly one lane owns the minimum
+    if (lane == 0) {
+        __stcg(a.gmin + qg, newmin);
+        atomicMax(a.g_best + qg, (uint32_t)(newmin >> 32));
+        if (a.stats) atomicAdd(a.stats + 4, 1ull);
+    }
+}
+
+// One round: up to 32 exact keys (one per lane, 0 = none) offered to query qg's list.
+__device__ __forceinline__ void list_offer(const ScanArgs &a, int qg, uint64_t key)
+{
+    const uint64_t gmin = __ldcg(a.gmin + qg);  // may be stale (smaller): only a pre-filter
+    uint32_t cand = __ballot_sync(0xffffffffu, key != 0ull && key > gmin);
+    if (!cand) return;
+    list_lock(a.glock + qg);
+    while (cand) {
+        const int l = __ffs(cand) - 1;
+        cand &= cand - 1;
+        list_insert_locked(a, qg, __shfl_sync(0xffffffffu, key, l));
+        __syncwarp();
+    }
+    list_unlock(a.glock + qg);
+}
+
+// Settle one query's hit buffer (whole warp): score the pending hits in the reference's
+// arithmetic and offer them to the global list; when the buffer overflowed during this
+// tile, score tile rows [tile_lo, tile_hi) exhaustively instead (nothing is ever lost).
+__device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c, int ql, int64_t tile_lo,
+                                            int64_t tile_hi)
 {
     const int lane = threadIdx.x & 31;
     const int raw_cnt = c.cnt[ql];
-    const bool overflow = raw_cnt > a.bufcap;
-    int cnt = overflow ? a.bufcap : raw_cnt;
+    const bool overflow = raw_cnt > a.cap;
+    const int cnt = overflow ? a.cap : raw_cnt;
+    const int qg = c.qid[ql];
     float q[kF];
 #pragma unroll
     for (int j = 0; j < kF; ++j) q[j] = c.qraw[ql * kF + j];
     const float qn = c.qn[ql];
     const int32_t ex = c.excl[ql];
-    unsigned rescored = 0;
-    for (int i = lane; i < cnt; i += 32) {
-        const uint64_t k = __ldcg(buf + i);
-        if ((uint32_t)(k >> 32) == kUnscored) {
-            const int64_t row = (int64_t)key_id(k) - a.id_base;
-            // entries of an overflowed tile are dropped here and found again by the re-scan
-            const bool drop = overflow && row >= tile_lo && row < tile_hi;
-            __stcg(buf + i, drop ? 0ull : exact_key(a, row, q, qn, ex));
-            ++rescored;
+    const uint32_t *hit = c.hit + (size_t)ql * a.cap;
+    for (int base = 0; base < cnt; base += 32) {
+        const int i = base + lane;
+        uint64_t key = 0ull;
+        if (i < cnt) key = exact_key(a, (int64_t)hit[i] - a.id_base, q, qn, ex);
+        list_offer(a, qg, key);
+    }
+    if (overflow) {
+        for (int64_t base = tile_lo; base < tile_hi; base += 32) {
+            const int64_t row = base + lane;
+            uint64_t key = 0ull;
+            if (row < tile_hi) key = exact_key(a, row, q, qn, ex);
+            list_offer(a, qg, key);
         }
     }
     __syncwarp();
-    uint64_t kth;
-    cnt = warp_keep_topk(buf, cnt, a.K, hist, &kth);
-    if (overflow) {
-        const int chunk = ((a.bufcap - a.K) / 32) * 32;
-        for (int64_t base = tile_lo; base < tile_hi; base += chunk) {
-            const int m = (int)min((int64_t)chunk, tile_hi - base);
-            for (int i = lane; i < m; i += 32) __stcg(buf + cnt + i, exact_key(a, base + i, q, qn, ex));
-            rescored += (m + 31 - lane) / 32;
-            __syncwarp();
-            cnt = warp_keep_topk(buf, cnt + m, a.K, hist, &kth);
-        }
-    }
     if (lane == 0) {
-        c.cnt[ql] = cnt;
-        if (kth != 0ull) {
-            const uint32_t b = (uint32_t)(kth >> 32);
-            if (b > c.best[ql]) {
-                c.best[ql] = b;
-                atomicMax(a.g_best + c.qid[ql], b);
-                c.nthr[ql] = neg_threshold(b);
-            }
+        c.cnt[ql] = 0;
+        const uint32_t b = __ldcg(a.g_best + qg);
+        if (b > c.best[ql]) {
+            c.best[ql] = b;
+            c.nthr[ql] = neg_threshold(b);
         }
         if (a.stats) {
             atomicAdd(a.stats + 1, 1ull);
             if (overflow) atomicAdd(a.stats + 2, 1ull);
+            atomicAdd(a.stats + 3, (unsigned long long)(cnt + (overflow ? (tile_hi - tile_lo) : 0)));
         }
     }
-    if (a.stats && rescored) atomicAdd(a.stats + 3, (unsigned long long)rescored);
     __syncwarp();
+}
+
+// Layout of the normalised store for a kernel shape (S songs per thread, THREADS per CTA):
+// a tile holds TS = S*THREADS consecutive songs; thread t owns songs t + s*THREADS and
+// multiplies them in pairs (2p, 2p+1).  The two songs of a pair are stored interleaved,
+// [a0 b0 a1 b1 ... a11 b11], so one 128-bit load yields two ready FFMA2 operands and a
+// warp's loads cover a contiguous 3 KB.  Float offset of feature j of local row `row`:
+__host__ __device__ __forceinline__ int64_t hat_offset(int64_t row, int j, int S, int THREADS)
+{
+    const int64_t TS = (int64_t)S * THREADS;
+    const int64_t tile = row / TS;
+    const int r = (int)(row - tile * TS);
+    const int s = r / THREADS, t = r - s * THREADS;
+    return ((tile * (S / 2) + (s >> 1)) * THREADS + t) * 24 + 2 * j + (s & 1);
 }
 
 // One filter pass of a thread's S songs against query record `ql` of the tile.
@@ -226,22 +286,20 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     c.cnt = reinterpret_cast<int *>(c.best + a.qt);
     c.excl = c.cnt + a.qt;
     c.qid = c.excl + a.qt;
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(c.qid + a.qt);
+    c.hit = reinterpret_cast<uint32_t *>(c.qid + a.qt);
 
-    const int G = gridDim.x;
-    const int nqt = (a.nq + a.qt - 1) / a.qt;
-    const int64_t U = (int64_t)nqt * a.n_tiles;
-    int64_t u = (U * blockIdx.x) / G;
-    const int64_t u_end = (U * (blockIdx.x + 1)) / G;
-    uint64_t *mybuf = a.cta_buf + (size_t)blockIdx.x * a.qt * a.bufcap;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t *my_hist = s_hist + warp * 256;
-    unsigned long long hits = 0;
+    unsigned hits = 0;
+    // this CTA's contiguous run of (query tile, song tile) units; kept in uniform
+    // arithmetic (no division) so the constant-bank query index stays warp-uniform and
+    // the FFMA2 query operand can live in a uniform register
+    int u = (int)blockIdx.x * a.upc + min((int)blockIdx.x, a.extra);
+    const int u_end = u + a.upc + ((int)blockIdx.x < a.extra ? 1 : 0);
+    int qtile = 0, t0 = u;
+    while (t0 >= a.n_tiles) { t0 -= a.n_tiles; ++qtile; }
 
     while (u < u_end) {
-        const int qtile = (int)(u / a.n_tiles);
-        const int t0 = (int)(u % a.n_tiles);
-        const int t1 = (int)min((int64_t)a.n_tiles, (int64_t)t0 + (u_end - u));
+        const int t1 = min(a.n_tiles, t0 + (u_end - u));
         const int q0 = qtile * a.qt;
         const int nql = min(a.qt, a.nq - q0);
 
@@ -262,15 +320,20 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         for (int tile = t0; tile < t1; ++tile) {
             const int64_t row0 = (int64_t)tile * TS + tid;
 
-            // ---- S songs of the normalised store into registers, as packed pairs
+            // ---- S songs of the normalised store into registers: S/2 interleaved pairs,
+            // six 128-bit loads each, every load two ready FFMA2 operands
             float2 fp[S / 2][kF];
+            {
+                const float4 *src = reinterpret_cast<const float4 *>(a.hat) + ((int64_t)tile * (S / 2) * THREADS + tid) * 6;
 #pragma unroll
-            for (int p = 0; p < S / 2; ++p) {
-                float r0[kF], r1[kF];
-                load_row12(a.hat, row0 + (int64_t)(2 * p) * THREADS, r0);
-                load_row12(a.hat, row0 + (int64_t)(2 * p + 1) * THREADS, r1);
+                for (int p = 0; p < S / 2; ++p) {
 #pragma unroll
-                for (int j = 0; j < kF; ++j) fp[p][j] = make_float2(r0[j], r1[j]);
+                    for (int c4 = 0; c4 < 6; ++c4) {
+                        const float4 v = __ldg(src + (int64_t)p * THREADS * 6 + c4);
+                        fp[p][2 * c4] = make_float2(v.x, v.y);
+                        fp[p][2 * c4 + 1] = make_float2(v.z, v.w);
+                    }
+                }
             }
 
             auto append = [&](int ql, const float2 (&acc)[S / 2]) {
@@ -283,10 +346,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                             const int64_t row = row0 + (int64_t)(2 * p + h) * THREADS;
                             if (row < a.n) {
                                 const int slot = atomicAdd(&c.cnt[ql], 1);
-                                if (slot < a.bufcap)
-                                    __stcg(mybuf + (size_t)ql * a.bufcap + slot,
-                                           ((uint64_t)kUnscored << 32) |
-                                               (uint64_t)(0xFFFFFFFFu - (uint32_t)(a.id_base + (int32_t)row)));
+                                if (slot < a.cap) c.hit[(size_t)ql * a.cap + slot] = (uint32_t)(a.id_base + (int32_t)row);
                                 ++hits;
                             }
                         }
@@ -294,38 +354,43 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 }
             };
 
-            // ---- the hot loop: one query per iteration
-            if (DEFER) {
-                // the sign test of query ql is consumed one iteration later, so its LOP3 tree
-                // overlaps the next query's FFMA2 stream; a hit re-runs the filter (rare path)
-                uint32_t m_prev = 0xffffffffu;
-#pragma unroll 2
-                for (int ql = 0; ql < nql; ++ql) {
-                    if ((int)m_prev >= 0) {
-                        float2 acc2[S / 2];
-                        filter_query<S>(fp, q0 + ql - 1, c.nthr[ql - 1], acc2);
-                        append(ql - 1, acc2);
+            // ---- the hot loop: one query per iteration, branch-free.  Iteration i only
+            // records whether any of the thread's S songs passed (one bit); the rare hits
+            // are picked up after every 32 queries by re-running the filter for the flagged
+            // queries, so the FFMA2 stream of consecutive queries is never split by a branch
+            // and every operand that depends on the query stays in uniform registers.
+            for (int qb = 0; qb < nql; qb += 32) {
+                const int qe = min(32, nql - qb);
+                uint32_t mask = 0;
+                if (DEFER) {
+#pragma unroll 4
+                    for (int i = 0; i < qe; ++i) {
+                        float2 acc[S / 2];
+                        const uint32_t m = filter_query<S>(fp, q0 + qb + i, c.nthr[qb + i], acc);
+                        mask |= ((~m) >> 31) << i;
                     }
-                    float2 acc[S / 2];
-                    m_prev = filter_query<S>(fp, q0 + ql, c.nthr[ql], acc);
-                }
-                if ((int)m_prev >= 0) {
-                    float2 acc2[S / 2];
-                    filter_query<S>(fp, q0 + nql - 1, c.nthr[nql - 1], acc2);
-                    append(nql - 1, acc2);
-                }
-            } else {
+                } else {
 #pragma unroll 2
-                for (int ql = 0; ql < nql; ++ql) {
+                    for (int i = 0; i < qe; ++i) {
+                        float2 acc[S / 2];
+                        const uint32_t m = filter_query<S>(fp, q0 + qb + i, c.nthr[qb + i], acc);
+                        mask |= ((~m) >> 31) << i;
+                    }
+                }
+                while (mask) {  // rare: this thread has a passing song for query qb + b
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int ql = qb + b;
                     float2 acc[S / 2];
-                    const uint32_t m = filter_query<S>(fp, q0 + ql, c.nthr[ql], acc);
-                    if ((int)m >= 0) append(ql, acc);
+                    filter_query<S>(fp, q0 + ql, c.nthr[ql], acc);
+                    append(ql, acc);
                 }
             }
             __syncthreads();
 
             // ---- tile epilogue: warp w looks after queries ql == w (mod WARPS), one lane each:
-            // adopt thresholds published by other CTAs, settle buffers that filled up.
+            // adopt thresholds published by other CTAs, settle hit buffers that filled up
+            // (every non-empty one after a segment's first tile, to warm the thresholds up).
             {
                 const int ql_mine = warp + WARPS * lane;
                 bool need = false;
@@ -335,38 +400,28 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                         c.best[ql_mine] = g;
                         c.nthr[ql_mine] = neg_threshold(g);
                     }
-                    need = c.cnt[ql_mine] > a.prune_at;
+                    const int cn = c.cnt[ql_mine];
+                    need = cn >= a.settle_at || (cn > 0 && (tile == t0 || tile == t1 - 1));
                 }
                 uint32_t todo = __ballot_sync(0xffffffffu, need);
                 const int64_t tile_lo = (int64_t)tile * TS;
                 const int64_t tile_hi = min(a.n, tile_lo + TS);
+                // start at a CTA-dependent lane so CTAs do not queue on the same list lock
+                const int rot = blockIdx.x & 31;
+                todo = __funnelshift_r(todo, todo, rot);
                 while (todo) {
-                    const int l = __ffs(todo) - 1;
+                    const int l = (__ffs(todo) - 1 + rot) & 31;
                     todo &= todo - 1;
-                    const int ql = warp + WARPS * l;
-                    warp_settle(a, c, mybuf + (size_t)ql * a.bufcap, ql, tile_lo, tile_hi, my_hist);
+                    warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi);
                 }
             }
             __syncthreads();
         }
-
-        // ---- segment epilogue: hand the exact survivors to the per-query pool
-        for (int ql = warp; ql < nql; ql += WARPS) {
-            if (c.cnt[ql] == 0) continue;
-            uint64_t *buf = mybuf + (size_t)ql * a.bufcap;
-            warp_settle(a, c, buf, ql, 0, 0, my_hist);
-            const int cnt = c.cnt[ql];
-            if (cnt == 0) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(a.pool_cnt + q0 + ql, cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            uint64_t *slab = a.pool + (size_t)(q0 + ql) * a.segs * a.K;
-            for (int i = lane; i < cnt; i += 32) slab[base + i] = __ldcg(buf + i);
-        }
-        __syncthreads();
         u += (t1 - t0);
+        t0 = 0;
+        ++qtile;
     }
-    if (a.stats && hits) atomicAdd(a.stats + 0, hits);
+    if (a.stats && hits) atomicAdd(a.stats + 0, (unsigned long long)hits);
 }
 
 }  // namespace sr

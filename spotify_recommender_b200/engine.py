@@ -23,7 +23,8 @@ EXPORTS = [
     "sr_engine_load_features_device", "sr_engine_song_count", "sr_engine_query_by_index",
     "sr_engine_query_by_vector", "sr_engine_query_by_index_dev", "sr_engine_query_by_vector_dev",
     "sr_engine_merge_topk_dev", "sr_engine_all_pairs_topk", "sr_engine_set_option", "sr_engine_get_stat",
-    "sr_engine_get_timing", "sr_engine_variant_name", "sr_engine_measure_fp32", "sr_engine_synchronize",
+    "sr_engine_get_timing", "sr_engine_variant_name", "sr_engine_measure_fp32", "sr_engine_selftest_div",
+    "sr_engine_synchronize",
 ]
 
 
@@ -68,6 +69,7 @@ def load_library() -> C.CDLL:
     L.sr_engine_variant_name.argtypes = [i32]
     L.sr_engine_variant_name.restype = C.c_char_p
     L.sr_engine_measure_fp32.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    L.sr_engine_selftest_div.argtypes = [vp, vp, vp, i32, vp]
     L.sr_engine_synchronize.argtypes = [vp]
     _lib = L
     return L
@@ -203,6 +205,13 @@ class Engine:
         t = C.c_double()
         self._check(self.L.sr_engine_measure_fp32(self.h, variant, C.byref(t)))
         return float(t.value)
+
+    def selftest_div(self, a, b):
+        a = np.ascontiguousarray(a, np.float32).ravel()
+        b = np.ascontiguousarray(b, np.float32).ravel()
+        out = np.empty_like(a)
+        self._check(self.L.sr_engine_selftest_div(self.h, _ptr(a), _ptr(b), a.size, _ptr(out)))
+        return out
 
     def synchronize(self) -> None:
         self._check(self.L.sr_engine_synchronize(self.h))

@@ -29,6 +29,29 @@ def assert_exact(got, want):
     assert np.array_equal(gs.view(np.uint32), ws.view(np.uint32)), "scores are not bit-identical to the oracle"
 
 
+def test_division_matches_ieee(eng):
+    """The device-side division (double Newton + one rounding, no subroutine call) is the
+    host's IEEE divss bit for bit: random operands over the whole exponent range, cosine-
+    like operands, subnormal quotients, and the special values."""
+    rng = np.random.default_rng(11)
+    n = 4_000_000
+    a = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    b = np.abs(rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32).view(np.float32))
+    b[~(b > 0)] = 1.0
+    a[:1_000_000] = (rng.random(1_000_000, dtype=np.float32) * 2 - 1) * b[:1_000_000]        # |q| <= 1
+    a[1_000_000:1_200_000] = b[1_000_000:1_200_000] * np.float32(1e-38) * rng.random(200_000, dtype=np.float32)
+    edge = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 1e-45, -1e-45, 3.4028235e38, 1.1754944e-38], np.float32)
+    eb = np.array([1e-8, 1.0, 3.0, np.inf, 3.4028235e38, 1.1754944e-38, 1e-45, 7.0, 0.1], np.float32)
+    a = np.concatenate([a, np.repeat(edge, eb.size)])
+    b = np.concatenate([b, np.tile(eb, edge.size)])
+    got = eng.selftest_div(a, b)
+    with np.errstate(all="ignore"):
+        want = a / b
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan)
+    assert np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32))
+
+
 CASES = load_golden()
 
 

@@ -34,6 +34,6 @@ for k in ks:
         tot = sum(e.timing(x)[0] for x in ("prep", "sample", "scan", "finalize")) / 2
         pairs = float(n) * nq
         tf = pairs * 24 / (ms / 2 * 1e-3) / 1e12
-        print("k=%d %-18s scan %.3f ms/batch (%d launches) total %.3f ms  scan %.1f TFLOP/s = %.1f%% of 74.4; hits/q %.0f settles/q %.2f rescans %d rescored/q %.0f" % (
+        print("k=%d %-18s scan %.3f ms/batch (%d launches) total %.3f ms  scan %.1f TFLOP/s = %.1f%% of 74.4; hits/q %.0f settles/q %.2f rescans %d rescored/q %.0f inserts/q %.0f" % (
             k, variant_names()[v], ms / 2, cnt // 2, tot, tf, 100 * tf / 74.4, e.stat("filter_hits") / 2 / nq, e.stat("settles") / 2 / nq,
-            e.stat("rescans"), e.stat("rescored") / 2 / nq), "| sample %.3f finalize %.3f prep %.3f" % (e.timing("sample")[0] / 2, e.timing("finalize")[0] / 2, e.timing("prep")[0] / 2), flush=True)
+            e.stat("rescans"), e.stat("rescored") / 2 / nq, e.stat("inserts") / 2 / nq), "| sample %.3f finalize %.3f prep %.3f" % (e.timing("sample")[0] / 2, e.timing("finalize")[0] / 2, e.timing("prep")[0] / 2), flush=True)
