@@ -117,9 +117,11 @@ __global__ void prep_queries_kernel(const PrepArgs a)
 }
 
 // ---- threshold bootstrap ---------------------------------------------------
-// One CTA per query scores a strided sample of the store EXACTLY and publishes the
-// K-th best sample score as the starting threshold: the K-th best of a subset never
-// exceeds the K-th best of the whole store, so the filter stays conservative.
+// One CTA per query scores a strided sample of the store EXACTLY and seeds the query's
+// global top-K list with the K best sample songs: the scan starts with a full list, so
+// its filter threshold is the sample's K-th best from the first tile on (a lower bound
+// of the final K-th best, hence conservative).  The scan meets the sample songs again;
+// list insertion ignores duplicates.
 struct SampleArgs {
     const float *raw;
     const float *nf;
@@ -128,15 +130,18 @@ struct SampleArgs {
     const float *qraw, *qn;
     const int32_t *exclude;
     int nq;
-    int m;       // sample size, power of two <= kSortCap, <= n
+    int m;       // sample size, power of two <= kSortCap, <= n, >= 2K
     int K;
+    uint64_t *glist;
+    int32_t *gcnt;
+    uint64_t *gmin;
     uint32_t *g_best;
 };
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) sample_threshold_kernel(const SampleArgs a)
 {
-    __shared__ uint32_t s_val[kSortCap];
+    __shared__ uint64_t s_key[kSortCap];
     const int qid = blockIdx.x;
     if (qid >= a.nq) return;
     float q[kF];
@@ -147,18 +152,20 @@ __global__ void __launch_bounds__(THREADS) sample_threshold_kernel(const SampleA
     const int64_t stride = a.n / a.m;
     for (int i = threadIdx.x; i < a.m; i += THREADS) {
         const int64_t row = (int64_t)i * stride;
+        const int32_t gid = a.id_base + (int32_t)row;
         float f[kF];
         load_row12(a.raw, row, f);
-        const float s = exact_score(f, a.nf[row], q, qn);
-        uint32_t o = f2ord(__fadd_rn(s, 0.0f));
-        if ((int32_t)(a.id_base + row) == ex) o = 0;  // self never counts
-        s_val[i] = o;
+        s_key[i] = (gid == ex) ? 0ull : make_key(exact_score(f, a.nf[row], q, qn), (uint32_t)gid);  // self never counts
     }
     __syncthreads();
-    bitonic_desc_u32<THREADS>(s_val, a.m);
+    bitonic_desc<THREADS>(s_key, a.m);
+    if (s_key[a.K - 1] == 0ull) return;  // fewer than K valid sample songs: leave the list empty
+    for (int r = threadIdx.x; r < a.K; r += THREADS) a.glist[(size_t)qid * a.K + r] = s_key[r];
     if (threadIdx.x == 0) {
-        const uint32_t o = s_val[a.K - 1];
-        if (o != 0) atomicMax(a.g_best + qid, o);
+        const uint64_t kth = s_key[a.K - 1];
+        a.gcnt[qid] = a.K;
+        a.gmin[qid] = kth;
+        a.g_best[qid] = (uint32_t)(kth >> 32);
     }
 }
 

@@ -316,7 +316,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             SampleArgs s;
             s.raw = e->d_raw; s.nf = e->d_nf; s.n = e->n; s.id_base = e->id_base;
             s.qraw = (float *)e->qraw.p; s.qn = (float *)e->qn.p; s.exclude = (int32_t *)e->excl.p;
-            s.nq = nq; s.m = m; s.K = K; s.g_best = (uint32_t *)e->gbest.p;
+            s.nq = nq; s.m = m; s.K = K; s.glist = (uint64_t *)e->glist.p; s.gcnt = (int32_t *)e->gcnt.p;
+            s.gmin = (uint64_t *)e->gmin.p; s.g_best = (uint32_t *)e->gbest.p;
             Scope sc(e, st, kSample);
             sample_threshold_kernel<256><<<nq, 256, 0, st>>>(s);
             SR_CUDA(cudaGetLastError());

@@ -64,7 +64,7 @@ struct ScanArgs {
 
 __host__ __device__ inline size_t scan_smem_bytes(int qt, int cap)
 {
-    return (size_t)qt * (kF + 6 + cap) * 4;
+    return (size_t)qt * (kF + 6 + cap) * 4 + 16;
 }
 
 // -T' for the filter; never +-0 (a -0 accumulator would read as "below").
@@ -96,7 +96,11 @@ __device__ __forceinline__ uint64_t exact_key(const ScanArgs &a, int64_t row, co
 __device__ __forceinline__ void list_lock(int32_t *lock)
 {
     if ((threadIdx.x & 31) == 0) {
-        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(100);
+        unsigned ns = 20;
+        while (atomicCAS(lock, 0, 1) != 0) {
+            __nanosleep(ns);
+            if (ns < 320) ns *= 2;
+        }
         __threadfence();
     }
     __syncwarp();
@@ -111,8 +115,19 @@ __device__ __forceinline__ void list_unlock(int32_t *lock)
     __syncwarp();
 }
 
-// Insert one exact key into query qg's list (whole warp, lock held).  Keeps the best K
-// keys; duplicates (a song met twice, e.g. after a tile re-scan) are ignored.
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+
+// Insert one exact key into query qg's list (whole warp, lock held), reading the list
+// from global memory: the path for K > 128.  Keeps the best K keys; duplicates (a song
+// met twice: seeded by the bootstrap sample, or after a tile re-scan) are ignored.
 __device__ __forceinline__ void list_insert_locked(const ScanArgs &a, int qg, uint64_t key)
 {
     const int lane = threadIdx.x & 31;
@@ -135,12 +150,7 @@ __device__ __forceinline__ void list_insert_locked(const ScanArgs &a, int qg, ui
         }
         if (n + 1 < a.K) return;
         // the list just became full: its minimum is the exact K-th best so far
-        uint64_t mn = m1 < key ? m1 : key;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const uint64_t o = __shfl_xor_sync(0xffffffffu, mn, off);
-            mn = o < mn ? o : mn;
-        }
+        const uint64_t mn = warp_min_u64(m1 < key ? m1 : key);
         if (lane == 0) {
             __stcg(a.gmin + qg, mn);
             atomicMax(a.g_best + qg, (uint32_t)(mn >> 32));
@@ -148,20 +158,10 @@ __device__ __forceinline__ void list_insert_locked(const ScanArgs &a, int qg, ui
         return;
     }
     // full list: the new key replaces the minimum if it beats it
-    uint64_t g1 = m1;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const uint64_t o = __shfl_xor_sync(0xffffffffu, g1, off);
-        g1 = o < g1 ? o : g1;
-    }
+    const uint64_t g1 = warp_min_u64(m1);
     if (key <= g1) return;
     // second smallest overall: lanes that own the minimum offer their runner-up
-    uint64_t g2 = (m1 == g1) ? m2 : m1;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const uint64_t o = __shfl_xor_sync(0xffffffffu, g2, off);
-        g2 = o < g2 ? o : g2;
-    }
+    const uint64_t g2 = warp_min_u64((m1 == g1) ? m2 : m1);
     const uint64_t newmin = key < g2 ? key : g2;
     if (m1 == g1) __stcg(list + p1, key);  // keys are unique: exactly one lane owns the minimum
     if (lane == 0) {
@@ -172,17 +172,75 @@ __device__ __forceinline__ void list_insert_locked(const ScanArgs &a, int qg, ui
 }
 
 // One round: up to 32 exact keys (one per lane, 0 = none) offered to query qg's list.
+// For K <= 128 the list is pulled into registers (4 keys per lane) once per lock, all
+// candidates are merged there, and it is written back once: the lock is held for two L2
+// round trips however many candidates there are.
 __device__ __forceinline__ void list_offer(const ScanArgs &a, int qg, uint64_t key)
 {
-    const uint64_t gmin = __ldcg(a.gmin + qg);  // may be stale (smaller): only a pre-filter
-    uint32_t cand = __ballot_sync(0xffffffffu, key != 0ull && key > gmin);
+    const int lane = threadIdx.x & 31;
+    const uint64_t stale = __ldcg(a.gmin + qg);  // may lag behind (smaller): only a pre-filter
+    uint32_t cand = __ballot_sync(0xffffffffu, key != 0ull && key > stale);
     if (!cand) return;
     list_lock(a.glock + qg);
-    while (cand) {
-        const int l = __ffs(cand) - 1;
-        cand &= cand - 1;
-        list_insert_locked(a, qg, __shfl_sync(0xffffffffu, key, l));
-        __syncwarp();
+    const uint64_t fresh = __ldcg(a.gmin + qg);
+    cand = __ballot_sync(0xffffffffu, key != 0ull && key > fresh);
+    if (cand && a.K > 128) {
+        while (cand) {
+            const int l = __ffs(cand) - 1;
+            cand &= cand - 1;
+            list_insert_locked(a, qg, __shfl_sync(0xffffffffu, key, l));
+            __syncwarp();
+        }
+    } else if (cand) {
+        uint64_t *list = a.glist + (size_t)qg * a.K;
+        int n = __ldcg(a.gcnt + qg);
+        uint64_t s[4];  // slot j of lane l <-> list[j * 32 + l]; empty slots hold ~0 (never the minimum)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] = (j * 32 + lane < n) ? __ldcg(list + j * 32 + lane) : ~0ull;
+        unsigned inserted = 0;
+        while (cand) {
+            const int l = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const uint64_t k = __shfl_sync(0xffffffffu, key, l);
+            const bool dup = (s[0] == k) | (s[1] == k) | (s[2] == k) | (s[3] == k);
+            if (__any_sync(0xffffffffu, dup)) continue;
+            if (n < a.K) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n == j * 32 + lane) s[j] = k;
+                ++n;
+                ++inserted;
+                continue;
+            }
+            uint64_t m = s[0] < s[1] ? s[0] : s[1];
+            const uint64_t m23 = s[2] < s[3] ? s[2] : s[3];
+            m = m < m23 ? m : m23;
+            const uint64_t g = warp_min_u64(m);
+            if (k <= g) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (s[j] == g) s[j] = k;  // keys are unique: one slot of one lane
+            ++inserted;
+        }
+        if (inserted) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (s[j] != ~0ull) __stcg(list + j * 32 + lane, s[j]);
+            if (n == a.K) {
+                uint64_t m = s[0] < s[1] ? s[0] : s[1];
+                const uint64_t m23 = s[2] < s[3] ? s[2] : s[3];
+                m = m < m23 ? m : m23;
+                const uint64_t g = warp_min_u64(m);
+                if (lane == 0) {
+                    __stcg(a.gmin + qg, g);
+                    atomicMax(a.g_best + qg, (uint32_t)(g >> 32));
+                }
+            }
+            if (lane == 0) {
+                __stcg(a.gcnt + qg, n);
+                if (a.stats) atomicAdd(a.stats + 4, (unsigned long long)inserted);
+            }
+        }
     }
     list_unlock(a.glock + qg);
 }
@@ -287,6 +345,13 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     c.excl = c.cnt + a.qt;
     c.qid = c.excl + a.qt;
     c.hit = reinterpret_cast<uint32_t *>(c.qid + a.qt);
+    // s_flag[tile % 3] != 0: some hit buffer filled up during that tile (set by the appending
+    // thread).  Three slots make the protocol race-free with ONE barrier per tile: slot t%3 is
+    // read right after tile t's barrier, cleared after tile t+1's barrier (every read is done),
+    // and next written during tile t+3, which starts after tile t+2's barrier.
+    int *s_flag = reinterpret_cast<int *>(c.hit + (size_t)a.qt * a.cap);
+    if (threadIdx.x < 3) s_flag[threadIdx.x] = 0;
+    int tphase = 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned hits = 0;
@@ -336,6 +401,13 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 }
             }
 
+            // a settle phase follows this tile if some hit buffer fills up (flagged by the thread
+            // whose append crosses the mark), and always after a segment's first and last tile
+            const bool forced = (tile == t0) || (tile == t1 - 1);
+            // thresholds other CTAs published meanwhile: requested now, consumed after the hot loop
+            uint32_t g_pre = 0;
+            if (warp + WARPS * lane < nql) g_pre = __ldcg(a.g_best + c.qid[warp + WARPS * lane]);
+
             auto append = [&](int ql, const float2 (&acc)[S / 2]) {
 #pragma unroll
                 for (int p = 0; p < S / 2; ++p) {
@@ -347,6 +419,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                             if (row < a.n) {
                                 const int slot = atomicAdd(&c.cnt[ql], 1);
                                 if (slot < a.cap) c.hit[(size_t)ql * a.cap + slot] = (uint32_t)(a.id_base + (int32_t)row);
+                                if (slot + 1 >= a.settle_at) s_flag[tphase] = 1;
                                 ++hits;
                             }
                         }
@@ -386,36 +459,45 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     append(ql, acc);
                 }
             }
-            __syncthreads();
-
             // ---- tile epilogue: warp w looks after queries ql == w (mod WARPS), one lane each:
-            // adopt thresholds published by other CTAs, settle hit buffers that filled up
-            // (every non-empty one after a segment's first tile, to warm the thresholds up).
+            // adopt thresholds published by other CTAs (g_pre was loaded before the hot loop, so
+            // its latency is hidden), and settle hit buffers that filled up -- every non-empty
+            // one after a segment's first and last tile.  One barrier when there is nothing to
+            // settle (threshold updates racing with other warps' reads are benign: any published
+            // threshold is a valid lower bound), two when there is.
             {
                 const int ql_mine = warp + WARPS * lane;
+                if (ql_mine < nql && g_pre > c.best[ql_mine]) {
+                    c.best[ql_mine] = g_pre;
+                    c.nthr[ql_mine] = neg_threshold(g_pre);
+                }
+            }
+            __syncthreads();  // all hits of this tile are in the buffers
+            const bool settle_phase = forced || (s_flag[tphase] != 0);
+            if (tid == 0) s_flag[tphase == 0 ? 2 : tphase - 1] = 0;  // the previous tile's slot
+            tphase = (tphase == 2) ? 0 : tphase + 1;
+            if (settle_phase) {
                 bool need = false;
-                if (ql_mine < nql) {
-                    const uint32_t g = __ldcg(a.g_best + c.qid[ql_mine]);
-                    if (g > c.best[ql_mine]) {
-                        c.best[ql_mine] = g;
-                        c.nthr[ql_mine] = neg_threshold(g);
+                {
+                    const int ql_mine = warp + WARPS * lane;
+                    if (ql_mine < nql) {
+                        const int cn = c.cnt[ql_mine];
+                        need = cn >= a.settle_at || (cn > 0 && (tile == t0 || tile == t1 - 1));
                     }
-                    const int cn = c.cnt[ql_mine];
-                    need = cn >= a.settle_at || (cn > 0 && (tile == t0 || tile == t1 - 1));
                 }
                 uint32_t todo = __ballot_sync(0xffffffffu, need);
                 const int64_t tile_lo = (int64_t)tile * TS;
                 const int64_t tile_hi = min(a.n, tile_lo + TS);
                 // start at a CTA-dependent lane so CTAs do not queue on the same list lock
-                const int rot = blockIdx.x & 31;
+                const int rot = (blockIdx.x * 5) & 31;
                 todo = __funnelshift_r(todo, todo, rot);
                 while (todo) {
                     const int l = (__ffs(todo) - 1 + rot) & 31;
                     todo &= todo - 1;
                     warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi);
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
         u += (t1 - t0);
         t0 = 0;
