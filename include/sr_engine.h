@@ -42,6 +42,8 @@ enum {
 
 typedef struct sr_engine sr_engine;
 
+#define SR_ENGINE_OWN_STREAM ((void *)(intptr_t)-1)
+
 /* Replaces the device probing / cublasCreate part of Recommender::initialize
  * (Recommender.cu:117-149).  device < 0 selects the current device. */
 int sr_engine_create(sr_engine **out, int device);
@@ -80,8 +82,9 @@ int sr_engine_query_by_vector(sr_engine *e, const float *qrows, const int32_t *e
                               int nq, int k, int32_t *out_idx, float *out_score);
 
 /* Device-resident variants: all pointers are device memory of this engine's
- * device, work is enqueued on `stream` (a cudaStream_t; NULL = the engine's own
- * stream) and NOT synchronised.  Used by the multi-GPU host (torch owns the
+ * device, work is enqueued on `stream` and NOT synchronised.  `stream` is a
+ * cudaStream_t (NULL = CUDA's legacy default stream, as everywhere in CUDA) or
+ * SR_ENGINE_OWN_STREAM for the engine's own non-blocking stream.  Used by the multi-GPU host (torch owns the
  * buffers and the NCCL exchange) and by bench.py's kernel-only timing. */
 int sr_engine_query_by_index_dev(sr_engine *e, const int32_t *d_qidx, int nq, int k,
                                  int32_t *d_out_idx, float *d_out_score, void *stream);
@@ -96,6 +99,12 @@ int sr_engine_query_by_vector_dev(sr_engine *e, const float *d_qrows, const int3
 int sr_engine_merge_topk_dev(sr_engine *e, const int32_t *d_idx, const float *d_score,
                              int parts, int nq, int k, int32_t *d_out_idx, float *d_out_score,
                              void *stream);
+
+/* First step of the row-sharded multi-GPU path: d_out (count x 12) receives the raw
+ * feature rows (Song::features, Song.h:26) of the global ids this engine owns and
+ * zeros for the others, so that one sum all-reduce over the shards hands every rank
+ * the whole query matrix.  Device pointers, stream-ordered. */
+int sr_engine_gather_rows_dev(sr_engine *e, const int32_t *d_ids, int count, float *d_out, void *stream);
 
 /* All-pairs neighbour table (BASELINE config 5): for every owned song with
  * global id in [q_lo, q_hi) its top-k neighbours, streamed through the same

@@ -18,6 +18,12 @@
  */
 #ifndef SR_RECOMMENDER_HPP
 #define SR_RECOMMENDER_HPP
+/* Also claim the reference header's include guard: a translation unit that sees this
+ * file first skips the reference's own class declaration (Recommender.h:1-2), which is
+ * how the reference's main.cpp is compiled against this class unmodified. */
+#ifndef RECOMMENDER_H
+#define RECOMMENDER_H
+#endif
 
 #include <string>
 #include <vector>

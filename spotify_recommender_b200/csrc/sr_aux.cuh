@@ -248,6 +248,23 @@ __global__ void __launch_bounds__(THREADS) merge_parts_kernel(const int32_t *idx
     }
 }
 
+// ---- row gather (multi-GPU query exchange) --------------------------------
+// out[i] = raw row of global id ids[i] when this store owns it, else zeros: summing the
+// outputs of all shards (one all-reduce) gives every rank the full query matrix.
+__global__ void gather_rows_kernel(const float *raw, int64_t n, int32_t id_base, const int32_t *ids, int count, float *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t local = (int64_t)ids[i] - id_base;
+    float4 *o = reinterpret_cast<float4 *>(out) + (size_t)i * 3;
+    if (local < 0 || local >= n) {
+        o[0] = o[1] = o[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float4 *p = reinterpret_cast<const float4 *>(raw) + local * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+}
+
 // ---- self-test hook: the engine's division, element-wise (tests only) ----------------
 __global__ void div_selftest_kernel(const float *a, const float *b, float *out, int n)
 {

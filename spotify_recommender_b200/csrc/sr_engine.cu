@@ -141,7 +141,7 @@ int ensure(sr_engine *e, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap) return SR_OK;
     if (b.p) {
-        SR_CUDA(cudaStreamSynchronize(e->stream));
+        SR_CUDA(cudaDeviceSynchronize());  // earlier passes may still run on a caller's stream
         SR_CUDA(cudaFree(b.p));
         e->device_bytes -= (int64_t)b.cap;
         b.p = nullptr;
@@ -364,6 +364,13 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     return SR_OK;
 }
 
+// SR_ENGINE_OWN_STREAM selects the engine's stream; anything else is a cudaStream_t
+// (NULL being CUDA's legacy default stream, which is what torch's default stream is).
+cudaStream_t pick_stream(sr_engine *e, void *stream)
+{
+    return stream == SR_ENGINE_OWN_STREAM ? e->stream : (cudaStream_t)stream;
+}
+
 int check_query_args(sr_engine *e, const void *q, int nq, int k, const void *out_idx)
 {
     if (!e) return SR_EINVAL;
@@ -543,7 +550,7 @@ int sr_engine_query_by_index_dev(sr_engine *e, const int32_t *d_qidx, int nq, in
     int rc = check_query_args(e, d_qidx, nq, k, d_out_idx);
     if (rc) return rc;
     SR_CUDA(cudaSetDevice(e->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    cudaStream_t st = pick_stream(e, stream);
     return run_device(e, d_qidx, nullptr, nullptr, nq, k, d_out_idx, d_out_score, st);
 }
 
@@ -553,7 +560,7 @@ int sr_engine_query_by_vector_dev(sr_engine *e, const float *d_qrows, const int3
     int rc = check_query_args(e, d_qrows, nq, k, d_out_idx);
     if (rc) return rc;
     SR_CUDA(cudaSetDevice(e->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    cudaStream_t st = pick_stream(e, stream);
     return run_device(e, nullptr, d_qrows, d_exclude, nq, k, d_out_idx, d_out_score, st);
 }
 
@@ -564,10 +571,23 @@ int sr_engine_merge_topk_dev(sr_engine *e, const int32_t *d_idx, const float *d_
     if (!d_idx || !d_score || !d_out_idx) return fail(e, SR_EINVAL, "merge: null pointer");
     if (parts <= 0 || nq <= 0 || k <= 0 || k > kKMax) return fail(e, SR_EINVAL, "merge: bad parts/nq/k");
     SR_CUDA(cudaSetDevice(e->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    cudaStream_t st = pick_stream(e, stream);
     Scope sc(e, st, kMerge);
     merge_parts_kernel<256><<<nq, 256, 0, st>>>(d_idx, d_score, parts, nq, k, d_out_idx, d_out_score);
     SR_CUDA(cudaGetLastError());
+    return SR_OK;
+}
+
+int sr_engine_gather_rows_dev(sr_engine *e, const int32_t *d_ids, int count, float *d_out, void *stream)
+{
+    if (!e) return SR_EINVAL;
+    if (!e->d_raw) return fail(e, SR_ESTATE, "no store loaded: call sr_engine_load_features first");
+    if (!d_ids || !d_out || count <= 0) return fail(e, SR_EINVAL, "gather_rows: bad arguments");
+    SR_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = pick_stream(e, stream);
+    gather_rows_kernel<<<(count + 127) / 128, 128, 0, st>>>(e->d_raw, e->n, e->id_base, d_ids, count, d_out);
+    SR_CUDA(cudaGetLastError());
+    ++e->launches;
     return SR_OK;
 }
 

@@ -22,7 +22,7 @@ EXPORTS = [
     "sr_engine_create", "sr_engine_destroy", "sr_engine_last_error", "sr_engine_load_features",
     "sr_engine_load_features_device", "sr_engine_song_count", "sr_engine_query_by_index",
     "sr_engine_query_by_vector", "sr_engine_query_by_index_dev", "sr_engine_query_by_vector_dev",
-    "sr_engine_merge_topk_dev", "sr_engine_all_pairs_topk", "sr_engine_set_option", "sr_engine_get_stat",
+    "sr_engine_merge_topk_dev", "sr_engine_gather_rows_dev", "sr_engine_all_pairs_topk", "sr_engine_set_option", "sr_engine_get_stat",
     "sr_engine_get_timing", "sr_engine_variant_name", "sr_engine_measure_fp32", "sr_engine_selftest_div",
     "sr_engine_synchronize",
 ]
@@ -62,6 +62,7 @@ def load_library() -> C.CDLL:
     L.sr_engine_query_by_index_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.sr_engine_query_by_vector_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     L.sr_engine_merge_topk_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    L.sr_engine_gather_rows_dev.argtypes = [vp, vp, i32, vp, vp]
     L.sr_engine_all_pairs_topk.argtypes = [vp, i64, i64, i32, vp, vp]
     L.sr_engine_set_option.argtypes = [vp, C.c_char_p, i64]
     L.sr_engine_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
@@ -95,6 +96,12 @@ def _ptr(a) -> C.c_void_p:
     if isinstance(a, int):
         return C.c_void_p(a)
     return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+def _stream(stream) -> C.c_void_p:
+    """None -> the engine's own stream (SR_ENGINE_OWN_STREAM); an int is a cudaStream_t
+    handle (0 = CUDA's legacy default stream, torch's default)."""
+    return C.c_void_p(-1 & (2 ** 64 - 1)) if stream is None else C.c_void_p(int(stream))
 
 
 class Engine:
@@ -173,19 +180,22 @@ class Engine:
         return out_i, out_s
 
     # -- queries, DEVICE buffers (stream-ordered, not synchronised) ------------
-    def query_by_index_dev(self, d_qidx, nq: int, k: int, d_out_idx, d_out_score=None, stream: int = 0) -> None:
+    def query_by_index_dev(self, d_qidx, nq: int, k: int, d_out_idx, d_out_score=None, stream: int | None = None) -> None:
         self._check(self.L.sr_engine_query_by_index_dev(self.h, _ptr(d_qidx), nq, k, _ptr(d_out_idx),
-                                                        _ptr(d_out_score), C.c_void_p(stream)))
+                                                        _ptr(d_out_score), _stream(stream)))
 
     def query_by_vector_dev(self, d_qrows, d_exclude, nq: int, k: int, d_out_idx, d_out_score=None,
-                            stream: int = 0) -> None:
+                            stream: int | None = None) -> None:
         self._check(self.L.sr_engine_query_by_vector_dev(self.h, _ptr(d_qrows), _ptr(d_exclude), nq, k,
-                                                         _ptr(d_out_idx), _ptr(d_out_score), C.c_void_p(stream)))
+                                                         _ptr(d_out_idx), _ptr(d_out_score), _stream(stream)))
 
     def merge_topk_dev(self, d_idx, d_score, parts: int, nq: int, k: int, d_out_idx, d_out_score=None,
-                       stream: int = 0) -> None:
+                       stream: int | None = None) -> None:
         self._check(self.L.sr_engine_merge_topk_dev(self.h, _ptr(d_idx), _ptr(d_score), parts, nq, k,
-                                                    _ptr(d_out_idx), _ptr(d_out_score), C.c_void_p(stream)))
+                                                    _ptr(d_out_idx), _ptr(d_out_score), _stream(stream)))
+
+    def gather_rows_dev(self, d_ids, count: int, d_out, stream: int | None = None) -> None:
+        self._check(self.L.sr_engine_gather_rows_dev(self.h, _ptr(d_ids), count, _ptr(d_out), _stream(stream)))
 
     # -- knobs / introspection -----------------------------------------------
     def set_option(self, key: str, value: int) -> None:

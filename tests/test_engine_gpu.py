@@ -191,3 +191,26 @@ def test_full_size_properties(eng, oracle):
     assert_exact(eng.query_by_index(q[spot], k), oracle.query_index(f, q[spot], k, threads=8))
     one_i, one_s = eng.query_by_index(q[777:778], k)
     assert np.array_equal(one_i[0], gi[777]) and np.array_equal(one_s[0], gs[777])
+
+
+def test_sharded_host_logic_single_rank_on_torch_stream(eng, oracle):
+    """ShardedRecommender with one rank, device buffers owned by torch, work enqueued on
+    torch's current (legacy default) stream, several batches back to back without a
+    synchronise in between: equals the oracle."""
+    import torch
+    from spotify_recommender_b200.sharded import ShardedRecommender
+    n, k = 300_000, 10
+    f = synth.features(n)
+    sh = ShardedRecommender(eng, n, device=torch.device("cuda", 0))
+    sh.load_shard(f)
+    qs = [(((np.arange(700, dtype=np.int64) + b * 700) * 7919 + 13) % n).astype(np.int32) for b in range(4)]
+    qd = [torch.from_numpy(q).cuda() for q in qs]
+    outs = []
+    for b in range(4):
+        oi, os_ = sh.query_by_index_dev(qd[b], k)
+        outs.append((oi.clone(), os_.clone()))
+    torch.cuda.synchronize()
+    for b in range(4):
+        want = oracle.query_index(f, qs[b], k, threads=8)
+        assert_exact((outs[b][0].cpu().numpy(), outs[b][1].cpu().numpy()), want)
+        assert_exact(sh.query_by_index(qs[b], k), want)

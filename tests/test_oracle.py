@@ -133,3 +133,31 @@ def test_live_reference_agrees(oracle):
             ci, _, cn = oracle.topk_canonical(sc, q, k)
             assert_same_up_to_ties(ci[:cn], got, sc, exclude=q)
         ref.close()
+
+
+def test_native_libraries_export_every_declared_symbol():
+    """The C-ABI library loads (no GPU needed) and exports every entry point include/sr_engine.h
+    declares; same for the C API around the C++ Recommender class."""
+    import ctypes, os, re
+    from spotify_recommender_b200 import build, engine
+    import recommender_lib
+    build.build_all()
+    hdr = open(os.path.join(build.ROOT, "include", "sr_engine.h")).read()
+    declared = sorted(set(re.findall(r"\b(sr_engine_[a-z0-9_]+)\s*\(", hdr)))
+    assert set(declared) == set(engine.EXPORTS)
+    lib = engine.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    rl = ctypes.CDLL(recommender_lib.SO)
+    for name in recommender_lib.EXPORTS:
+        assert hasattr(rl, name), name
+
+
+def test_engine_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a box without an sm_100 device construction raises."""
+    import torch
+    from spotify_recommender_b200.engine import Engine, EngineError
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(EngineError):
+        Engine(0)

@@ -1,0 +1,130 @@
+"""The drop-in boundary on the GPU: the C++ `Recommender` class (include/sr_recommender.hpp)
+against the unmodified reference class (oracle/_ref/libref_cpu.so, and the reference's own
+cuBLAS path rebuilt for sm_100a, libref_gpu.so), and the reference CLI built on the engine."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import assert_same_up_to_ties
+from oracle_lib import ORACLE_DIR, Reference
+from spotify_recommender_b200 import synth
+
+pytestmark = pytest.mark.gpu
+SCORE_TOL = 1e-6  # north_star: scores within 1e-6 absolute of the reference's cuBLAS path
+
+
+@pytest.fixture(scope="module")
+def names():
+    base = ["Shape of You", "shape of you (Remix)", "Blinding Lights", "BLINDING LIGHTS", "Stay", "stay with me",
+            "Track", "Bohemian Rhapsody", "bohemian", "", "Levitating", "Peaches"]
+    return [base[i % len(base)] + (f" {i}" if i >= len(base) else "") for i in range(3000)]
+
+
+def test_class_mirrors_reference_api(oracle, names):
+    from recommender_lib import HostRecommender
+    f = synth.features(3000)
+    ids = [f"id{i % 2900:05d}" for i in range(3000)]  # the last 100 ids repeat earlier ones: first match wins
+    rec = HostRecommender(f, ids=ids, names=names)
+    assert rec.gpu_enabled()
+    # by index: canonical order == oracle
+    for q, k in ((0, 10), (17, 1), (2999, 100), (5, 4000)):
+        want, _ = oracle.query_index(f, [q], min(k, 1024))
+        got = rec.by_index(q, k)
+        assert np.array_equal(got, want[0][want[0] >= 0])
+    # error behaviour (reference Recommender.cu:276-284, :358-361, :367-370): empty result
+    assert rec.by_index(-1, 5).size == 0 and rec.by_index(3000, 5).size == 0 and rec.by_index(3, 0).size == 0
+    assert rec.by_id("nope", 5).size == 0 and rec.by_name("no such song anywhere", 5).size == 0
+    # lookups: first exact track_id; first case-insensitive exact name, else first substring
+    assert rec.find_id("id00050") == 50 and rec.find_id("id00005") == 5
+    assert rec.find_name("BLINDING lights") == 2
+    assert rec.find_name("stay") == 4
+    assert rec.find_name("rhapsody") == 7
+    assert rec.find_name("with me") == 5
+    assert rec.find_name("Levitating 22") == 22
+    assert np.array_equal(rec.by_name("blinding lights", 7), rec.by_index(2, 7))
+    assert np.array_equal(rec.by_id("id00050", 7), rec.by_index(50, 7))
+    rec.close()
+
+
+@pytest.mark.skipif(not Reference.available(), reason="oracle/_ref not built")
+def test_against_live_reference_class(oracle, names):
+    """Same songs through the unmodified reference (CPU path) and through the B200 class:
+    identical up to the reference's tie artefact; identical lookups."""
+    from recommender_lib import HostRecommender
+    n = 20_000
+    f = synth.features(n)
+    ref = Reference(f)                 # names "Track <i>", ids "id<i>" (ref_harness.cpp)
+    rec = HostRecommender(f)           # same defaults
+    for q in (0, 13, 7919, n - 1):
+        sc = oracle.scores(f, f[q])
+        assert_same_up_to_ties(rec.by_index(q, 25), ref.by_index(q, 25), sc, exclude=q)
+    for name in ("Track 500", "track 77", "TRACK 1999", "rack 31", "9999"):
+        a, b = rec.by_name(name, 10), ref.by_name(name, 10)
+        assert a.size == b.size == 10
+        qi = rec.find_name(name)
+        assert_same_up_to_ties(a, b, oracle.scores(f, f[qi]), exclude=qi)
+    for tid in ("id0", "id19999", "id123"):
+        qi = rec.find_id(tid)
+        assert_same_up_to_ties(rec.by_id(tid, 10), ref.by_id(tid, 10), oracle.scores(f, f[qi]), exclude=qi)
+    assert rec.by_id("id20000", 10).size == 0 and ref.by_id("id20000", 10).size == 0
+    ref.close(); rec.close()
+
+
+@pytest.mark.skipif(not Reference.available(gpu=True), reason="oracle/_ref/libref_gpu.so not built")
+def test_against_reference_cublas_path(oracle):
+    """north_star: scores within 1e-6 of the reference's cuBLAS SGEMV path rebuilt for
+    sm_100a; index lists equal wherever neighbouring scores are further apart than the
+    reference's own GPU-vs-CPU noise."""
+    from spotify_recommender_b200.engine import Engine
+    n, k = 300_000, 10
+    f = synth.uniform(n)
+    ref = Reference(f, gpu=True)
+    if not ref.gpu_enabled():
+        pytest.skip("reference fell back to its CPU path on this box")
+    eng = Engine(0)
+    eng.load_features(f)
+    q = synth.query_indices(24, n)
+    gi, gs = eng.query_by_index(q, k)
+    mism = 0
+    for j, qi in enumerate(q):
+        rsc = ref.scores(int(qi))                     # cuBLAS dot + the reference's two kernels
+        assert np.max(np.abs(rsc[gi[j]] - gs[j])) <= SCORE_TOL
+        ri = ref.by_index(int(qi), k)
+        if not np.array_equal(ri, gi[j]):
+            mism += 1
+            # any disagreement must sit inside a near-tie of the reference's own scores
+            d = np.where(ri != gi[j])[0]
+            assert np.all(np.abs(rsc[ri[d]] - rsc[gi[j][d]]) <= 2 * SCORE_TOL)
+    print(f"cuBLAS-path ordered-list mismatches: {mism}/{len(q)} (reference GPU-vs-CPU noise floor)")
+    ref.close(); eng.close()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ORACLE_DIR, "_ref", "recommender_b200")),
+                    reason="reference CLI on the engine not built (oracle/Makefile, needs /root/reference)")
+def test_reference_cli_end_to_end(tmp_path):
+    """synthetic Spotify-schema CSV -> reference --preprocess -> songs_data.bin -> the
+    reference's main.cpp linked against the B200 class prints the same recommendations as
+    the reference's own CPU build."""
+    cpu = os.path.join(ORACLE_DIR, "_ref", "recommender_cpu")
+    b200 = os.path.join(ORACLE_DIR, "_ref", "recommender_b200")
+    csv = tmp_path / "tracks.csv"
+    synth.spotify_csv(str(csv), n_rows=5000)
+    env = dict(os.environ, OMP_NUM_THREADS="1")  # the reference's preprocess is only deterministic at 1 thread
+    out = subprocess.run([cpu, "--preprocess", str(csv)], cwd=tmp_path, env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and (tmp_path / "songs_data.bin").exists(), out.stdout + out.stderr
+    assert "4999" in out.stdout  # one row has an empty name (README.md:280 behaviour)
+
+    def ids(binary, *args):
+        r = subprocess.run([binary, *args], cwd=tmp_path, env=env, capture_output=True, text=True)
+        return r.returncode, re.findall(r"^\s+ID:\s+(\S+)\s*$", r.stdout, flags=re.M), r.stdout + r.stderr
+
+    for args in (("--song", "Track 500", "-n", "10"), ("--id", "id0001234", "-n", "5"), ("--song", "track 42")):
+        rc_a, ids_a, log_a = ids(cpu, *args)
+        rc_b, ids_b, log_b = ids(b200, *args)
+        assert rc_a == 0 and rc_b == 0, log_b
+        assert len(ids_b) > 1 and ids_a == ids_b, (ids_a, ids_b)
+    rc, _, _ = ids(b200, "--song", "definitely not a track name")
+    assert rc == 1
