@@ -67,7 +67,7 @@ struct PrepArgs {
     int32_t *excl;
     int32_t *gcnt, *glock;    // per-query list state, reset here
     uint64_t *gmin;
-    uint32_t *g_best;
+    uint32_t *g_best, *gbound;
     int32_t *bad_index;       // set to 1 when a gather id is not owned by this store
 };
 
@@ -114,6 +114,7 @@ __global__ void prep_queries_kernel(const PrepArgs a)
     a.glock[q] = 0;
     a.gmin[q] = 0ull;
     a.g_best[q] = kOrdNegInf;
+    a.gbound[q] = 0xFFFFFFFFu;  // min-reduced by the bound pass
 }
 
 // ---- threshold bootstrap ---------------------------------------------------

@@ -8,7 +8,7 @@
 namespace sr {
 
 constexpr int kF = 12;            // reference Song.h:12 FEATURE_COUNT
-constexpr int kQTMax = 128;       // queries resident in shared memory per CTA
+constexpr int kQTMax = 256;       // queries resident in shared memory per CTA
 constexpr int kSortCap = 4096;    // keys sorted per pass by one CTA in finalize / sample
 constexpr int kKMax = 1024;       // largest supported top-K
 constexpr int kRowPad = 36864;    // store rows are padded to a multiple of every tile size
@@ -17,6 +17,9 @@ constexpr int kRowPad = 36864;    // store rows are padded to a multiple of ever
 // (u = 2^-24, 3.2e-6) for regular rows and queries: DESIGN.md "filter slack".
 // Every filter threshold is the exact running K-th best minus kEps.
 constexpr float kEps = 5.0e-6f;
+// bound pass: a filter score computed from a zero start is within 26u + 14u < 2.4e-6 of the
+// oracle's score of the same pair; lowered by this before it is used as a K-th-best bound
+constexpr float kBoundSlack = 4.0e-6f;
 // rows / queries whose exact norm is outside [kNormLo, kNormHi] (and not 0) are
 // "irregular": the bound above assumes no under/overflow, so they carry NaN in
 // the normalised store / record, always pass the filter and are scored exactly.

@@ -25,6 +25,7 @@ thread_local std::string g_create_error;
 // ---- scan kernel shapes --------------------------------------------------------
 typedef cudaError_t (*ScanLaunch)(const ScanArgs &, int grid, size_t smem, cudaStream_t st);
 typedef cudaError_t (*ScanOcc)(int *ctas_per_sm, size_t smem);
+typedef cudaError_t (*BoundLaunch)(const ScanArgs &, int nb, int stride, int grid, size_t smem, cudaStream_t st);
 
 template <int S, int T, int M, bool D>
 cudaError_t launch_scan(const ScanArgs &a, int grid, size_t smem, cudaStream_t st)
@@ -44,14 +45,22 @@ cudaError_t occ_scan(int *ctas, size_t smem)
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k, T, smem);
 }
 
+template <int S, int T, int M>
+cudaError_t launch_bound(const ScanArgs &a, int nb, int stride, int grid, size_t smem, cudaStream_t st)
+{
+    bound_kernel<S, T, M><<<grid, T, smem, st>>>(a, nb, stride);
+    return cudaGetLastError();
+}
+
 struct Variant {
     const char *name;
-    int S, threads;
+    int S, threads, ctas;
     ScanLaunch launch;
     ScanOcc occ;
+    BoundLaunch bound;
 };
 #define SR_VARIANT(S, T, M, D) \
-    {"S" #S "xT" #T "x" #M "-" #D, S, T, launch_scan<S, T, M, D>, occ_scan<S, T, M, D>}
+    {"S" #S "xT" #T "x" #M "-" #D, S, T, M, launch_scan<S, T, M, D>, occ_scan<S, T, M, D>, launch_bound<S, T, M>}
 const Variant kVariants[] = {
     SR_VARIANT(8, 256, 2, false),
     SR_VARIANT(8, 256, 2, true),
@@ -64,8 +73,8 @@ const Variant kVariants[] = {
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
-enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kNumKernels };
-const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge"};
+enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kPilot, kBound, kNumKernels };
+const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge", "pilot", "bound"};
 
 struct DevBuf {
     void *p = nullptr;
@@ -88,15 +97,17 @@ struct sr_engine {
     int hat_variant = -1;  // kernel shape d_hat is laid out for
 
     // options
-    int variant = 0;
+    int variant = 3;
     int qt_opt = kQTMax;
     int batch = 8192;
     int sample = -1;  // -1: automatic
+    bool pilot = false; // pilot passes before the full scan
+    bool bound = true;  // bound pass (filter-speed threshold bootstrap)
     int hit_cap = 128; // hit-buffer entries per query in shared memory
     bool profile = false;
 
     // batch workspace (grow-only)
-    DevBuf qraw, qn, qhat, excl, gbest, gcnt, glock, gmin, glist, out_idx, out_score, qin, exin;
+    DevBuf qraw, qn, qhat, excl, gbest, gbound, gcnt, glock, gmin, glist, out_idx, out_score, qin, exin;
     unsigned long long *d_stats = nullptr;  // [8]
     unsigned long long *d_irregular = nullptr;
     int32_t *d_flag = nullptr;
@@ -111,8 +122,8 @@ struct sr_engine {
         int kernel;
     };
     std::vector<Timed> pending;
-    double ms_total[kNumKernels] = {0, 0, 0, 0, 0};
-    int64_t ms_count[kNumKernels] = {0, 0, 0, 0, 0};
+    double ms_total[kNumKernels] = {0, 0, 0, 0, 0, 0, 0};
+    int64_t ms_count[kNumKernels] = {0, 0, 0, 0, 0, 0, 0};
     int64_t device_bytes = 0;
 };
 
@@ -275,7 +286,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     const int nqt0 = (gsize + qt_cap - 1) / qt_cap;
     const int qt = (gsize + nqt0 - 1) / nqt0;
     const int nqt = (gsize + qt - 1) / qt;
-    const int cap = e->hit_cap;
+    int cap = e->hit_cap;  // shrink the hit buffers until the shape's CTAs per SM fit in shared memory
+    while (cap > 32 && scan_smem_bytes(qt, cap) * v.ctas > 200 * 1024) cap /= 2;
     const size_t smem = scan_smem_bytes(qt, cap);
     int ctas = 0;
     SR_CUDA(v.occ(&ctas, smem));
@@ -291,6 +303,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->qhat, (size_t)nq * kF * 4))) return rc;
     if ((rc = ensure(e, e->excl, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gbest, (size_t)nq * 4))) return rc;
+    if ((rc = ensure(e, e->gbound, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gcnt, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->glock, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gmin, (size_t)nq * 8))) return rc;
@@ -302,13 +315,19 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         p.qidx = d_qidx; p.qrows_in = d_qrows; p.excl_in = d_excl; p.nq = nq;
         p.qraw = (float *)e->qraw.p; p.qn = (float *)e->qn.p; p.qhat = (float *)e->qhat.p;
         p.excl = (int32_t *)e->excl.p; p.gcnt = (int32_t *)e->gcnt.p; p.glock = (int32_t *)e->glock.p;
-        p.gmin = (uint64_t *)e->gmin.p; p.g_best = (uint32_t *)e->gbest.p; p.bad_index = e->d_flag;
+        p.gmin = (uint64_t *)e->gmin.p; p.g_best = (uint32_t *)e->gbest.p; p.gbound = (uint32_t *)e->gbound.p;
+        p.bad_index = e->d_flag;
         Scope sc(e, st, kPrep);
         prep_queries_kernel<<<(nq + 127) / 128, 128, 0, st>>>(p);
         SR_CUDA(cudaGetLastError());
     }
-    // threshold bootstrap
+    // threshold bootstrap: the bound pass (filter speed, per query group, below) when the store
+    // has enough full tiles, else / additionally the exact sample
+    const int64_t full_tiles = e->n / TS;
+    const int nb = K + 1;
+    const bool use_bound = e->bound && full_tiles >= 4 * (int64_t)nb;
     int m = e->sample;
+    if (m < 0 && use_bound) m = 0;
     if (m < 0) m = std::min(kSortCap, std::max(1024, 2 * pow2_floor((int64_t)K * 32 - 1)));
     if (m > 0) {
         m = std::min(m, pow2_floor(e->n / 4));  // only worth it on stores much larger than the sample
@@ -334,20 +353,38 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.glist = (uint64_t *)e->glist.p + (size_t)g0 * K; a.gcnt = (int32_t *)e->gcnt.p + g0;
         a.gmin = (uint64_t *)e->gmin.p + g0; a.glock = (int32_t *)e->glock.p + g0;
         a.g_best = (uint32_t *)e->gbest.p + g0;
+        a.gbound = (uint32_t *)e->gbound.p + g0;
         a.stats = e->d_stats;
         const int gnqt = (gq + qt - 1) / qt;
-        const int64_t gunits = (int64_t)gnqt * n_tiles;
-        const int ggrid = (int)std::min<int64_t>(grid, gunits);
-        a.upc = (int)(gunits / ggrid);
-        a.extra = (int)(gunits % ggrid);
         std::lock_guard<std::mutex> lock(g_bank_mutex);
         cudaEvent_t &ev = g_bank_event[e->device & 63];
         if (!ev) SR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         else SR_CUDA(cudaStreamWaitEvent(st, ev, 0));
         SR_CUDA(cudaMemcpyToSymbolAsync(c_qhat, (const float *)e->qhat.p + (size_t)g0 * kF, (size_t)gq * kF * 4, 0,
                                         cudaMemcpyDeviceToDevice, st));
-        {
-            Scope sc(e, st, kScan);
+        if (use_bound) {
+            const int bgrid = (int)std::min<int64_t>((int64_t)e->sm_count * v.ctas, (int64_t)gnqt * nb);
+            Scope sc(e, st, kBound);
+            SR_CUDA(v.bound(a, nb, (int)(full_tiles / nb), bgrid, (size_t)qt * 4, st));
+            bound_finish_kernel<<<(gq + 127) / 128, 128, 0, st>>>(a.gbound, a.g_best, gq);
+            SR_CUDA(cudaGetLastError());
+            ++e->launches;
+        }
+        // Pilot passes: the same kernel over 8, then 64 evenly spaced song tiles first.  They cost
+        // < 2 % of the work and leave every query with the exact top-K of a 10^4..10^5-song sample,
+        // so the full pass starts with a selective threshold on every CTA at once (the full pass
+        // meets the pilot tiles again; list insertion ignores duplicates).
+        const int passes[3] = {e->pilot ? 8 : 0, e->pilot ? 64 : 0, n_tiles};
+        for (int pi = 0; pi < 3; ++pi) {
+            const int pt = passes[pi];
+            if (pt <= 0 || (pi < 2 && n_tiles < 8 * pt)) continue;
+            a.n_tiles = pt;
+            a.tile_stride = (pi < 2) ? n_tiles / pt : 1;
+            const int64_t gunits = (int64_t)gnqt * pt;
+            const int ggrid = (int)std::min<int64_t>(grid, gunits);
+            a.upc = (int)(gunits / ggrid);
+            a.extra = (int)(gunits % ggrid);
+            Scope sc(e, st, pi < 2 ? kPilot : kScan);
             SR_CUDA(v.launch(a, ggrid, smem, st));
         }
         SR_CUDA(cudaEventRecord(ev, st));
@@ -480,7 +517,7 @@ void sr_engine_destroy(sr_engine *e)
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto &t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gcnt, &e->glock, &e->gmin,
+    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gcnt, &e->glock, &e->gmin,
                       &e->glist, &e->out_idx, &e->out_score, &e->qin, &e->exin};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -647,6 +684,10 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
         if (value > kSortCap || (value > 0 && (value & (value - 1))))
             return fail(e, SR_EINVAL, "sample must be 0, negative (auto) or a power of two <= %d", kSortCap);
         e->sample = (int)value;
+    } else if (!strcmp(key, "bound")) {
+        e->bound = value != 0;
+    } else if (!strcmp(key, "pilot")) {
+        e->pilot = value != 0;
     } else if (!strcmp(key, "hit_cap")) {
         if (value < 32 || value > 1024 || value % 32) return fail(e, SR_EINVAL, "hit_cap must be a multiple of 32 in [32, 1024]");
         e->hit_cap = (int)value;

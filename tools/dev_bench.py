@@ -16,6 +16,10 @@ feats = torch.rand((n, 12), device="cuda", generator=g)
 feats = torch.floor(feats * 1000) / 1000
 e = Engine(0)
 e.load_features(feats)
+import os
+for kv in os.environ.get("SR_OPTS", "").split(","):
+    if "=" in kv:
+        e.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 print("store ready", time.time() - t0, "s; fp32 peak FFMA2 %.1f FFMA %.1f unfused %.1f TF" % (e.measure_fp32(1), e.measure_fp32(0), e.measure_fp32(2)), flush=True)
 q = synth.query_indices(nq, n)
 dq = torch.from_numpy(q).cuda()
@@ -31,9 +35,9 @@ for k in ks:
             e.query_by_index_dev(dq, nq, k, oi, os_)
         e.synchronize()
         ms, cnt = e.timing("scan")
-        tot = sum(e.timing(x)[0] for x in ("prep", "sample", "scan", "finalize")) / 2
+        tot = sum(e.timing(x)[0] for x in ("prep", "sample", "pilot", "bound", "scan", "finalize")) / 2
         pairs = float(n) * nq
         tf = pairs * 24 / (ms / 2 * 1e-3) / 1e12
         print("k=%d %-18s scan %.3f ms/batch (%d launches) total %.3f ms  scan %.1f TFLOP/s = %.1f%% of 74.4; hits/q %.0f settles/q %.2f rescans %d rescored/q %.0f inserts/q %.0f" % (
             k, variant_names()[v], ms / 2, cnt // 2, tot, tf, 100 * tf / 74.4, e.stat("filter_hits") / 2 / nq, e.stat("settles") / 2 / nq,
-            e.stat("rescans"), e.stat("rescored") / 2 / nq, e.stat("inserts") / 2 / nq), "| sample %.3f finalize %.3f prep %.3f" % (e.timing("sample")[0] / 2, e.timing("finalize")[0] / 2, e.timing("prep")[0] / 2), flush=True)
+            e.stat("rescans"), e.stat("rescored") / 2 / nq, e.stat("inserts") / 2 / nq), "| bound %.3f pilot %.3f sample %.3f finalize %.3f prep %.3f" % (e.timing("bound")[0] / 2, e.timing("pilot")[0] / 2, e.timing("sample")[0] / 2, e.timing("finalize")[0] / 2, e.timing("prep")[0] / 2), flush=True)
