@@ -103,6 +103,7 @@ struct sr_engine {
     int sample = -1;  // -1: automatic
     bool pilot = false; // pilot passes before the full scan
     bool bound = true;  // bound pass (filter-speed threshold bootstrap)
+    int settle_at = 0;  // 0: hit_cap / 4
     int hit_cap = 128; // hit-buffer entries per query in shared memory
     bool profile = false;
 
@@ -349,7 +350,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.n_tiles = n_tiles;
         a.qraw = (float *)e->qraw.p + (size_t)g0 * kF; a.qn = (float *)e->qn.p + g0;
         a.exclude = (int32_t *)e->excl.p + g0; a.nq = gq; a.qt = qt;
-        a.K = K; a.cap = cap; a.settle_at = std::max(1, cap / 4);
+        a.K = K; a.cap = cap; a.settle_at = e->settle_at > 0 ? std::min(e->settle_at, cap) : std::max(1, cap / 4);
         a.glist = (uint64_t *)e->glist.p + (size_t)g0 * K; a.gcnt = (int32_t *)e->gcnt.p + g0;
         a.gmin = (uint64_t *)e->gmin.p + g0; a.glock = (int32_t *)e->glock.p + g0;
         a.g_best = (uint32_t *)e->gbest.p + g0;
@@ -363,9 +364,13 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         SR_CUDA(cudaMemcpyToSymbolAsync(c_qhat, (const float *)e->qhat.p + (size_t)g0 * kF, (size_t)gq * kF * 4, 0,
                                         cudaMemcpyDeviceToDevice, st));
         if (use_bound) {
-            const int bgrid = (int)std::min<int64_t>((int64_t)e->sm_count * v.ctas, (int64_t)gnqt * nb);
+            // finer query tiles than the scan's, so that the few sample tiles still occupy every SM
+            ScanArgs b = a;
+            b.qt = std::min(qt, 64);
+            const int bnqt = (gq + b.qt - 1) / b.qt;
+            const int bgrid = (int)std::min<int64_t>((int64_t)e->sm_count * v.ctas, (int64_t)bnqt * nb);
             Scope sc(e, st, kBound);
-            SR_CUDA(v.bound(a, nb, (int)(full_tiles / nb), bgrid, (size_t)qt * 4, st));
+            SR_CUDA(v.bound(b, nb, (int)(full_tiles / nb), bgrid, (size_t)b.qt * 4, st));
             bound_finish_kernel<<<(gq + 127) / 128, 128, 0, st>>>(a.gbound, a.g_best, gq);
             SR_CUDA(cudaGetLastError());
             ++e->launches;
@@ -384,6 +389,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             const int ggrid = (int)std::min<int64_t>(grid, gunits);
             a.upc = (int)(gunits / ggrid);
             a.extra = (int)(gunits % ggrid);
+            // about eight early settlers per query tile (all of them when the lists are long)
+            a.force_mod = (K > 32) ? 1 : std::max(1, ggrid / gnqt / 8);
             Scope sc(e, st, pi < 2 ? kPilot : kScan);
             SR_CUDA(v.launch(a, ggrid, smem, st));
         }
@@ -684,6 +691,9 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
         if (value > kSortCap || (value > 0 && (value & (value - 1))))
             return fail(e, SR_EINVAL, "sample must be 0, negative (auto) or a power of two <= %d", kSortCap);
         e->sample = (int)value;
+    } else if (!strcmp(key, "settle_at")) {
+        if (value < 0 || value > 1024) return fail(e, SR_EINVAL, "settle_at must be in [0, 1024]");
+        e->settle_at = (int)value;
     } else if (!strcmp(key, "bound")) {
         e->bound = value != 0;
     } else if (!strcmp(key, "pilot")) {

@@ -54,6 +54,7 @@ struct ScanArgs {
     int K;
     int cap;                 // hit-buffer entries per query (shared memory)
     int settle_at;           // settle a query's hit buffer once it holds this many
+    int force_mod;           // CTAs with blockIdx % force_mod == 0 settle after their first tile too
     // global per-query exact top-K state, shared by every CTA (lock-protected)
     uint64_t *glist;         // [nq][K] exact keys, unordered
     int32_t *gcnt;           // [nq] valid keys in glist
@@ -106,6 +107,16 @@ __device__ __forceinline__ void list_lock(int32_t *lock)
         __threadfence();
     }
     __syncwarp();
+}
+// one attempt; true when the lock was taken (whole warp gets the same answer)
+__device__ __forceinline__ bool list_trylock(int32_t *lock)
+{
+    int ok = 0;
+    if ((threadIdx.x & 31) == 0) {
+        ok = (atomicCAS(lock, 0, 1) == 0);
+        if (ok) __threadfence();
+    }
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
 __device__ __forceinline__ void list_unlock(int32_t *lock)
 {
@@ -177,15 +188,17 @@ __device__ __forceinline__ void list_insert_locked(const ScanArgs &a, int qg, ui
 // acquisition.  For K <= 128 the list is pulled into registers (4 keys per lane), all
 // candidates are merged there and it is written back once: the lock is held for two L2
 // round trips plus ~30 instructions per surviving candidate.
-__device__ __forceinline__ void list_offer4(const ScanArgs &a, int qg, const uint64_t (&key)[4])
+// Returns false (nothing done) when `blocking` is off and another CTA holds the lock.
+__device__ __forceinline__ bool list_offer4(const ScanArgs &a, int qg, const uint64_t (&key)[4], bool blocking)
 {
     const int lane = threadIdx.x & 31;
     const uint64_t stale = __ldcg(a.gmin + qg);  // may lag behind (smaller): only a pre-filter
     bool mine = false;
 #pragma unroll
     for (int r = 0; r < 4; ++r) mine |= (key[r] != 0ull && key[r] > stale);
-    if (!__any_sync(0xffffffffu, mine)) return;
-    list_lock(a.glock + qg);
+    if (!__any_sync(0xffffffffu, mine)) return true;
+    if (blocking) list_lock(a.glock + qg);
+    else if (!list_trylock(a.glock + qg)) return false;
     const uint64_t fresh = __ldcg(a.gmin + qg);
     uint32_t cand[4];
     uint32_t any = 0;
@@ -262,14 +275,17 @@ __device__ __forceinline__ void list_offer4(const ScanArgs &a, int qg, const uin
         }
     }
     list_unlock(a.glock + qg);
+    return true;
 }
 
 // Settle one query's hit buffer (whole warp): score the pending hits in the reference's
 // arithmetic (four independent load chains per lane) and offer them to the global list;
 // when the buffer overflowed during this tile, score tile rows [tile_lo, tile_hi)
 // exhaustively instead (nothing is ever lost).
-__device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c, int ql, int64_t tile_lo,
-                                            int64_t tile_hi)
+// With `blocking` off, a buffer of <= 128 hits whose list lock is busy is left untouched and
+// false is returned: the caller moves on to its next query and comes back later.
+__device__ __forceinline__ bool warp_settle(const ScanArgs &a, const QueryCtx &c, int ql, int64_t tile_lo,
+                                            int64_t tile_hi, bool blocking)
 {
     const int lane = threadIdx.x & 31;
     const int raw_cnt = c.cnt[ql];
@@ -282,6 +298,7 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
     const float qn = c.qn[ql];
     const int32_t ex = c.excl[ql];
     const uint32_t *hit = c.hit + (size_t)ql * a.cap;
+    if (overflow || cnt > 128) blocking = true;  // multi-chunk settles never back off
     for (int base = 0; base < cnt; base += 128) {
         uint64_t key[4];
 #pragma unroll
@@ -289,7 +306,7 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
             const int i = base + r * 32 + lane;
             key[r] = (i < cnt) ? exact_key(a, (int64_t)hit[i] - a.id_base, q, qn, ex) : 0ull;
         }
-        list_offer4(a, qg, key);
+        if (!list_offer4(a, qg, key, blocking)) return false;
     }
     if (overflow) {
         for (int64_t base = tile_lo; base < tile_hi; base += 128) {
@@ -299,7 +316,7 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
                 const int64_t row = base + r * 32 + lane;
                 key[r] = (row < tile_hi) ? exact_key(a, row, q, qn, ex) : 0ull;
             }
-            list_offer4(a, qg, key);
+            list_offer4(a, qg, key, true);
         }
     }
     __syncwarp();
@@ -317,6 +334,7 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
         }
     }
     __syncwarp();
+    return true;
 }
 
 // Layout of the normalised store for a kernel shape (S songs per thread, THREADS per CTA):
@@ -430,7 +448,11 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 
             // a settle phase follows this tile if some hit buffer fills up (flagged by the thread
             // whose append crosses the mark), and always after a segment's first and last tile
-            const bool forced = (tile == t0) || (tile == t1 - 1);
+            // every CTA settles everything after its last tile; one CTA in force_mod (about eight
+            // per query tile) also after its first tile, which is enough to fill the lists and
+            // publish selective thresholds early without every CTA of a query tile queueing on
+            // the same list locks
+            const bool forced = (tile == t1 - 1) || (tile == t0 && (int)(blockIdx.x % (unsigned)a.force_mod) == 0);
             // thresholds other CTAs published meanwhile: requested now, consumed after the hot loop
             uint32_t g_pre = 0;
             if (warp + WARPS * lane < nql) g_pre = __ldcg(a.g_best + c.qid[warp + WARPS * lane]);
@@ -509,7 +531,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     const int ql_mine = warp + WARPS * lane;
                     if (ql_mine < nql) {
                         const int cn = c.cnt[ql_mine];
-                        need = cn >= a.settle_at || (cn > 0 && (tile == t0 || tile == t1 - 1));
+                        need = cn >= a.settle_at || (cn > 0 && forced);
                     }
                 }
                 uint32_t todo = __ballot_sync(0xffffffffu, need);
@@ -520,12 +542,17 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 const int per_warp = (nql + WARPS - 1) / WARPS;
                 const int rot = (int)(blockIdx.x % (unsigned)per_warp);
                 const uint32_t lo_mask = (1u << rot) - 1u;
-                uint32_t first = todo & ~lo_mask, second = todo & lo_mask;
-                while (first | second) {
+                uint32_t first = todo & ~lo_mask, second = todo & lo_mask, retry = 0;
+                while (first | second) {  // first round: skip queries whose list is locked by another CTA
                     uint32_t &w = first ? first : second;
                     const int l = __ffs(w) - 1;
                     w &= w - 1;
-                    warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi);
+                    if (!warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi, false)) retry |= 1u << l;
+                }
+                while (retry) {  // second round: wait for them
+                    const int l = __ffs(retry) - 1;
+                    retry &= retry - 1;
+                    warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi, true);
                 }
                 __syncthreads();
             }
