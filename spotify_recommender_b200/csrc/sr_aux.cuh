@@ -65,8 +65,7 @@ struct PrepArgs {
     int nq;
     float *qraw, *qn, *qhat;  // outputs
     int32_t *excl;
-    int32_t *gcnt, *glock;    // per-query list state, reset here
-    uint64_t *gmin;
+    int32_t *pool_cnt;        // per-query state, reset here
     uint32_t *g_best, *gbound;
     int32_t *bad_index;       // set to 1 when a gather id is not owned by this store
 };
@@ -110,19 +109,15 @@ __global__ void prep_queries_kernel(const PrepArgs a)
         // pair passes the filter and is scored exactly
         a.qhat[(size_t)q * kF + j] = regular ? (float)((double)v[j] * inv) : qnan;
     }
-    a.gcnt[q] = 0;
-    a.glock[q] = 0;
-    a.gmin[q] = 0ull;
+    a.pool_cnt[q] = 0;
     a.g_best[q] = kOrdNegInf;
     a.gbound[q] = 0xFFFFFFFFu;  // min-reduced by the bound pass
 }
 
-// ---- threshold bootstrap ---------------------------------------------------
-// One CTA per query scores a strided sample of the store EXACTLY and seeds the query's
-// global top-K list with the K best sample songs: the scan starts with a full list, so
-// its filter threshold is the sample's K-th best from the first tile on (a lower bound
-// of the final K-th best, hence conservative).  The scan meets the sample songs again;
-// list insertion ignores duplicates.
+// ---- threshold bootstrap (stores too small for the bound pass) -----------------------------
+// One CTA per query scores a strided sample of the store EXACTLY and publishes the K-th best
+// sample score as the starting threshold: the K-th best of a subset never exceeds the K-th
+// best of the whole store, so the filter stays conservative.
 struct SampleArgs {
     const float *raw;
     const float *nf;
@@ -133,16 +128,13 @@ struct SampleArgs {
     int nq;
     int m;       // sample size, power of two <= kSortCap, <= n, >= 2K
     int K;
-    uint64_t *glist;
-    int32_t *gcnt;
-    uint64_t *gmin;
     uint32_t *g_best;
 };
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) sample_threshold_kernel(const SampleArgs a)
 {
-    __shared__ uint64_t s_key[kSortCap];
+    __shared__ uint32_t s_val[kSortCap];
     const int qid = blockIdx.x;
     if (qid >= a.nq) return;
     float q[kF];
@@ -153,20 +145,18 @@ __global__ void __launch_bounds__(THREADS) sample_threshold_kernel(const SampleA
     const int64_t stride = a.n / a.m;
     for (int i = threadIdx.x; i < a.m; i += THREADS) {
         const int64_t row = (int64_t)i * stride;
-        const int32_t gid = a.id_base + (int32_t)row;
         float f[kF];
         load_row12(a.raw, row, f);
-        s_key[i] = (gid == ex) ? 0ull : make_key(exact_score(f, a.nf[row], q, qn), (uint32_t)gid);  // self never counts
+        const float s = exact_score(f, a.nf[row], q, qn);
+        uint32_t o = f2ord(__fadd_rn(s, 0.0f));
+        if ((int32_t)(a.id_base + row) == ex) o = 0;  // self never counts
+        s_val[i] = o;
     }
     __syncthreads();
-    bitonic_desc<THREADS>(s_key, a.m);
-    if (s_key[a.K - 1] == 0ull) return;  // fewer than K valid sample songs: leave the list empty
-    for (int r = threadIdx.x; r < a.K; r += THREADS) a.glist[(size_t)qid * a.K + r] = s_key[r];
+    bitonic_desc_u32<THREADS>(s_val, a.m);
     if (threadIdx.x == 0) {
-        const uint64_t kth = s_key[a.K - 1];
-        a.gcnt[qid] = a.K;
-        a.gmin[qid] = kth;
-        a.g_best[qid] = (uint32_t)(kth >> 32);
+        const uint32_t o = s_val[a.K - 1];
+        if (o != 0) atomicMax(a.g_best + qid, o);
     }
 }
 
@@ -199,11 +189,11 @@ __device__ __forceinline__ int block_select_topk(uint64_t *s_keys, int total, in
     return valid;
 }
 
-// One CTA per query: the scan's exact (unordered) top-K list -> ordered output rows.
+// One CTA per query: the exact survivors of every scan segment -> ordered top-K rows.
 struct FinalArgs {
-    const uint64_t *glist;
-    const int32_t *gcnt;
-    int nq, K;
+    const uint64_t *pool;
+    const int32_t *pool_cnt;
+    int nq, K, segs;
     int32_t *out_idx;    // [nq][K]
     float *out_score;    // [nq][K] or null
 };
@@ -214,8 +204,8 @@ __global__ void __launch_bounds__(THREADS) finalize_kernel(const FinalArgs a)
     __shared__ uint64_t s_keys[kSortCap];
     const int q = blockIdx.x;
     if (q >= a.nq) return;
-    const uint64_t *slab = a.glist + (size_t)q * a.K;
-    const int P = min(a.gcnt[q], a.K);
+    const uint64_t *slab = a.pool + (size_t)q * a.segs * a.K;
+    const int P = a.pool_cnt[q];
     int valid = 0;
     if (P > 0) valid = block_select_topk<THREADS>(s_keys, P, a.K, [&](int i) { return slab[i]; });
     for (int r = threadIdx.x; r < a.K; r += THREADS) {

@@ -108,7 +108,7 @@ struct sr_engine {
     bool profile = false;
 
     // batch workspace (grow-only)
-    DevBuf qraw, qn, qhat, excl, gbest, gbound, gcnt, glock, gmin, glist, out_idx, out_score, qin, exin;
+    DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, pool_cnt, pool, out_idx, out_score, qin, exin;
     unsigned long long *d_stats = nullptr;  // [8]
     unsigned long long *d_irregular = nullptr;
     int32_t *d_flag = nullptr;
@@ -283,13 +283,20 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     // query groups (what fits the constant bank), evenly filled; then query tiles inside a group
     const int groups = (nq + kConstQueries - 1) / kConstQueries;
     const int gsize = (nq + groups - 1) / groups;
-    const int qt_cap = std::max(1, std::min(e->qt_opt, kQTMax));
+    // queries per tile and hit-buffer size: as large as asked for and as fits in shared memory
+    // next to the CTA's exact top-K lists (qt x K keys)
+    int qt_cap = std::max(1, std::min(e->qt_opt, kQTMax));
+    int cap = e->hit_cap;
+    const size_t smem_budget = (size_t)200 * 1024 / v.ctas;
+    while (scan_smem_bytes(qt_cap, cap, K) > smem_budget) {
+        if (cap > 32) cap /= 2;
+        else if (qt_cap > 8) qt_cap /= 2;
+        else return fail(e, SR_EINVAL, "k = %d does not fit the scan kernel's shared memory", K);
+    }
     const int nqt0 = (gsize + qt_cap - 1) / qt_cap;
     const int qt = (gsize + nqt0 - 1) / nqt0;
     const int nqt = (gsize + qt - 1) / qt;
-    int cap = e->hit_cap;  // shrink the hit buffers until the shape's CTAs per SM fit in shared memory
-    while (cap > 32 && scan_smem_bytes(qt, cap) * v.ctas > 200 * 1024) cap /= 2;
-    const size_t smem = scan_smem_bytes(qt, cap);
+    const size_t smem = scan_smem_bytes(qt, cap, K);
     int ctas = 0;
     SR_CUDA(v.occ(&ctas, smem));
     if (ctas < 1) return fail(e, SR_ECUDA, "scan kernel %s does not fit one SM (smem %zu)", v.name, smem);
@@ -297,6 +304,12 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if (units > 0x7fffffffLL) return fail(e, SR_EINVAL, "store too large for one pass (%lld work units)", (long long)units);
     const int grid = (int)std::min<int64_t>((int64_t)e->sm_count * ctas, units);
     e->scan_grid = grid;
+    int upc_min = 0x7fffffff;  // fewest units per CTA over the groups of this pass => most segments per query tile
+    for (int g0 = 0; g0 < nq; g0 += gsize) {
+        const int64_t gunits = (int64_t)((std::min(gsize, nq - g0) + qt - 1) / qt) * n_tiles;
+        upc_min = (int)std::min<int64_t>(upc_min, std::max<int64_t>(1, gunits / std::min<int64_t>(grid, gunits)));
+    }
+    const int segs = scan_segs(n_tiles, upc_min);
 
     int rc;
     if ((rc = ensure(e, e->qraw, (size_t)nq * kF * 4))) return rc;
@@ -305,18 +318,18 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->excl, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gbest, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gbound, (size_t)nq * 4))) return rc;
-    if ((rc = ensure(e, e->gcnt, (size_t)nq * 4))) return rc;
-    if ((rc = ensure(e, e->glock, (size_t)nq * 4))) return rc;
-    if ((rc = ensure(e, e->gmin, (size_t)nq * 8))) return rc;
-    if ((rc = ensure(e, e->glist, (size_t)nq * K * 8))) return rc;
+    if ((rc = ensure(e, e->gslot, (size_t)nq * K * 8))) return rc;
+    if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
+    if ((rc = ensure(e, e->pool, (size_t)nq * segs * K * 8))) return rc;
 
+    SR_CUDA(cudaMemsetAsync(e->gslot.p, 0, (size_t)nq * K * 8, st));
     {
         PrepArgs p;
         p.raw_store = e->d_raw; p.n = e->n; p.id_base = e->id_base;
         p.qidx = d_qidx; p.qrows_in = d_qrows; p.excl_in = d_excl; p.nq = nq;
         p.qraw = (float *)e->qraw.p; p.qn = (float *)e->qn.p; p.qhat = (float *)e->qhat.p;
-        p.excl = (int32_t *)e->excl.p; p.gcnt = (int32_t *)e->gcnt.p; p.glock = (int32_t *)e->glock.p;
-        p.gmin = (uint64_t *)e->gmin.p; p.g_best = (uint32_t *)e->gbest.p; p.gbound = (uint32_t *)e->gbound.p;
+        p.excl = (int32_t *)e->excl.p; p.pool_cnt = (int32_t *)e->pool_cnt.p;
+        p.g_best = (uint32_t *)e->gbest.p; p.gbound = (uint32_t *)e->gbound.p;
         p.bad_index = e->d_flag;
         Scope sc(e, st, kPrep);
         prep_queries_kernel<<<(nq + 127) / 128, 128, 0, st>>>(p);
@@ -336,8 +349,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             SampleArgs s;
             s.raw = e->d_raw; s.nf = e->d_nf; s.n = e->n; s.id_base = e->id_base;
             s.qraw = (float *)e->qraw.p; s.qn = (float *)e->qn.p; s.exclude = (int32_t *)e->excl.p;
-            s.nq = nq; s.m = m; s.K = K; s.glist = (uint64_t *)e->glist.p; s.gcnt = (int32_t *)e->gcnt.p;
-            s.gmin = (uint64_t *)e->gmin.p; s.g_best = (uint32_t *)e->gbest.p;
+            s.nq = nq; s.m = m; s.K = K; s.g_best = (uint32_t *)e->gbest.p;
             Scope sc(e, st, kSample);
             sample_threshold_kernel<256><<<nq, 256, 0, st>>>(s);
             SR_CUDA(cudaGetLastError());
@@ -351,8 +363,9 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.qraw = (float *)e->qraw.p + (size_t)g0 * kF; a.qn = (float *)e->qn.p + g0;
         a.exclude = (int32_t *)e->excl.p + g0; a.nq = gq; a.qt = qt;
         a.K = K; a.cap = cap; a.settle_at = e->settle_at > 0 ? std::min(e->settle_at, cap) : std::max(1, cap / 4);
-        a.glist = (uint64_t *)e->glist.p + (size_t)g0 * K; a.gcnt = (int32_t *)e->gcnt.p + g0;
-        a.gmin = (uint64_t *)e->gmin.p + g0; a.glock = (int32_t *)e->glock.p + g0;
+        a.gslot = (uint64_t *)e->gslot.p + (size_t)g0 * K;
+        a.pool = (uint64_t *)e->pool.p + (size_t)g0 * segs * K; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
+        a.segs = segs;
         a.g_best = (uint32_t *)e->gbest.p + g0;
         a.gbound = (uint32_t *)e->gbound.p + g0;
         a.stats = e->d_stats;
@@ -389,8 +402,6 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             const int ggrid = (int)std::min<int64_t>(grid, gunits);
             a.upc = (int)(gunits / ggrid);
             a.extra = (int)(gunits % ggrid);
-            // about eight early settlers per query tile (all of them when the lists are long)
-            a.force_mod = (K > 32) ? 1 : std::max(1, ggrid / gnqt / 8);
             Scope sc(e, st, pi < 2 ? kPilot : kScan);
             SR_CUDA(v.launch(a, ggrid, smem, st));
         }
@@ -398,8 +409,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     }
     {
         FinalArgs f;
-        f.glist = (uint64_t *)e->glist.p; f.gcnt = (int32_t *)e->gcnt.p;
-        f.nq = nq; f.K = K; f.out_idx = d_out_idx; f.out_score = d_out_score;
+        f.pool = (uint64_t *)e->pool.p; f.pool_cnt = (int32_t *)e->pool_cnt.p;
+        f.nq = nq; f.K = K; f.segs = segs; f.out_idx = d_out_idx; f.out_score = d_out_score;
         Scope sc(e, st, kFinalize);
         finalize_kernel<256><<<nq, 256, 0, st>>>(f);
         SR_CUDA(cudaGetLastError());
@@ -524,8 +535,8 @@ void sr_engine_destroy(sr_engine *e)
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto &t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gcnt, &e->glock, &e->gmin,
-                      &e->glist, &e->out_idx, &e->out_score, &e->qin, &e->exin};
+    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->pool_cnt, &e->pool,
+                      &e->out_idx, &e->out_score, &e->qin, &e->exin};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->d_raw) cudaFree(e->d_raw);

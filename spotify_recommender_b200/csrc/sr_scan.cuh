@@ -16,11 +16,14 @@
 //     "filter slack": |acc - (oracle score - T')| < kEps for regular rows; NaN
 //     rows/queries always pass).  One LOP3 tree over the sign bits per S songs.
 //   hit (rare): the song id is appended, unscored, to the query's candidate buffer.
-//   settle (rare, warp-cooperative, at tile borders): unscored candidates are
-//     scored in the reference's own arithmetic (Recommender.cu:263-271, unfused
-//     mul/add, sqrt*qn, IEEE divide, clamp) from the RAW store; a radix select
-//     keeps the best K exact keys (score desc, id asc), which raises T' and is
-//     published to the other CTAs working on the same queries (g_best).
+//   settle (rare, warp-cooperative, at tile borders): pending ids are scored in the
+//     reference's own arithmetic (Recommender.cu:263-271, unfused mul/add, sqrt*qn, IEEE
+//     divide, clamp) from the RAW store and merged into this CTA's exact top-K list of the
+//     query (shared memory; score desc, id asc).  A full list's K-th key is a lower bound of
+//     the final K-th best; it raises T' and is published to the other CTAs working on the
+//     same queries (g_best, atomicMax -- no locks anywhere).
+//   flush: at the end of its run over a query tile the CTA appends its lists to the
+//     per-query pool; finalize_kernel merges the pool into the ordered top-K.
 //   rescan (pathological tiles only: mass ties, NaN queries): when a tile yields
 //     more hits than the buffer holds, the owning warp scores the tile exactly.
 //
@@ -54,21 +57,25 @@ struct ScanArgs {
     int K;
     int cap;                 // hit-buffer entries per query (shared memory)
     int settle_at;           // settle a query's hit buffer once it holds this many
-    int force_mod;           // CTAs with blockIdx % force_mod == 0 settle after their first tile too
-    // global per-query exact top-K state, shared by every CTA (lock-protected)
-    uint64_t *glist;         // [nq][K] exact keys, unordered
-    int32_t *gcnt;           // [nq] valid keys in glist
-    uint64_t *gmin;          // [nq] smallest key of a FULL list (the exact K-th best), else 0
-    int32_t *glock;          // [nq] 0 free / 1 held
+    // per-query exact survivors of every CTA segment, merged by finalize_kernel
+    uint64_t *pool;          // [nq][segs * K] exact keys
+    int32_t *pool_cnt;       // [nq] keys in the pool slab
+    int segs;                // slab capacity in segments (scan_segs())
     uint32_t *g_best;        // [nq] orderable score: best known lower bound of the final K-th best
+    uint64_t *gslot;         // [nq][K] lock-free global feedback: slot (id mod K) holds the best exact
+                             // key any CTA has found among the songs with that residue (atomicMax)
     uint32_t *gbound;        // [nq] bound pass: min over K+1 sample tiles of the tile's best filter score
     unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] inserts
 };
 
-__host__ __device__ inline size_t scan_smem_bytes(int qt, int cap)
+__host__ __device__ inline size_t scan_smem_bytes(int qt, int cap, int K)
 {
-    return (size_t)qt * (kF + 6 + cap) * 4 + 16;
+    return (size_t)qt * K * 8 + (size_t)qt * (kF + 7 + cap) * 4 + 16;
 }
+
+// CTA runs (segments) that can touch one query tile = slab capacity of the pool, in lists:
+// a query tile is n_tiles consecutive units and every CTA owns at least `upc` of them
+__host__ __device__ inline int scan_segs(int n_tiles, int upc) { return (n_tiles + upc - 1) / upc + 2; }
 
 // -T' for the filter; never +-0 (a -0 accumulator would read as "below").
 __device__ __forceinline__ float neg_threshold(uint32_t best_ord)
@@ -79,10 +86,11 @@ __device__ __forceinline__ float neg_threshold(uint32_t best_ord)
 }
 
 struct QueryCtx {  // shared-memory views of one query tile
+    uint64_t *list;  // [qt][K] this CTA's exact top-K so far (unordered), per query
     float *nthr, *qraw, *qn;
     uint32_t *best;
-    int *cnt, *excl, *qid;
-    uint32_t *hit;  // [qt][cap] global ids that passed the filter, not yet scored
+    int *cnt, *lcnt, *excl, *qid;
+    uint32_t *hit;   // [qt][cap] global ids that passed the filter, not yet scored
 };
 
 // exact key of one (query, row) pair, 0 when the row is the excluded song
@@ -95,39 +103,7 @@ __device__ __forceinline__ uint64_t exact_key(const ScanArgs &a, int64_t row, co
     return make_key(exact_score(f, __ldg(a.nf + row), q, qn), (uint32_t)gid);
 }
 
-// ---- the global per-query list ------------------------------------------------------
-__device__ __forceinline__ void list_lock(int32_t *lock)
-{
-    if ((threadIdx.x & 31) == 0) {
-        unsigned ns = 20;
-        while (atomicCAS(lock, 0, 1) != 0) {
-            __nanosleep(ns);
-            if (ns < 320) ns *= 2;
-        }
-        __threadfence();
-    }
-    __syncwarp();
-}
-// one attempt; true when the lock was taken (whole warp gets the same answer)
-__device__ __forceinline__ bool list_trylock(int32_t *lock)
-{
-    int ok = 0;
-    if ((threadIdx.x & 31) == 0) {
-        ok = (atomicCAS(lock, 0, 1) == 0);
-        if (ok) __threadfence();
-    }
-    return __shfl_sync(0xffffffffu, ok, 0) != 0;
-}
-__device__ __forceinline__ void list_unlock(int32_t *lock)
-{
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-        __threadfence();
-        atomicExch(lock, 0);
-    }
-    __syncwarp();
-}
-
+// ---- the CTA-local per-query list (shared memory, one warp at a time per query) ---------
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v)
 {
 #pragma unroll
@@ -138,106 +114,36 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v)
     return v;
 }
 
-// Insert one exact key into query qg's list (whole warp, lock held), reading the list
-// from global memory: the path for K > 128.  Keeps the best K keys; duplicates (a song
-// met twice: seeded by the bootstrap sample, or after a tile re-scan) are ignored.
-__device__ __forceinline__ void list_insert_locked(const ScanArgs &a, int qg, uint64_t key)
+// Up to 128 exact keys (four per lane, 0 = none) merged into the list of query ql: the best
+// K keys survive; duplicates (a song met twice after a tile re-scan) are ignored.  For
+// K <= 128 the list is pulled into registers (4 keys per lane), merged there and written
+// back once; longer lists are updated in place, one candidate at a time.  Returns the
+// list's minimum when it is full (the exact K-th best of the songs this CTA has seen), else 0.
+__device__ __forceinline__ uint64_t list_merge4(const ScanArgs &a, const QueryCtx &c, int ql, const uint64_t (&key)[4])
 {
     const int lane = threadIdx.x & 31;
-    uint64_t *list = a.glist + (size_t)qg * a.K;
-    const int n = __ldcg(a.gcnt + qg);
-    // per-lane two smallest keys (and where the smallest sits), plus duplicate detection
-    uint64_t m1 = ~0ull, m2 = ~0ull;
-    int p1 = -1;
-    bool dup = false;
-    for (int i = lane; i < n; i += 32) {
-        const uint64_t k = __ldcg(list + i);
-        dup |= (k == key);
-        if (k < m1) { m2 = m1; m1 = k; p1 = i; } else if (k < m2) { m2 = k; }
-    }
-    if (__any_sync(0xffffffffu, dup)) return;
-    if (n < a.K) {
-        if (lane == 0) {
-            __stcg(list + n, key);
-            __stcg(a.gcnt + qg, n + 1);
-        }
-        if (n + 1 < a.K) return;
-        // the list just became full: its minimum is the exact K-th best so far
-        const uint64_t mn = warp_min_u64(m1 < key ? m1 : key);
-        if (lane == 0) {
-            __stcg(a.gmin + qg, mn);
-            atomicMax(a.g_best + qg, (uint32_t)(mn >> 32));
-        }
-        return;
-    }
-    // full list: the new key replaces the minimum if it beats it
-    const uint64_t g1 = warp_min_u64(m1);
-    if (key <= g1) return;
-    // second smallest overall: lanes that own the minimum offer their runner-up
-    const uint64_t g2 = warp_min_u64((m1 == g1) ? m2 : m1);
-    const uint64_t newmin = key < g2 ? key : g2;
-    if (m1 == g1) __stcg(list + p1, key);  // keys are unique: exactly one lane owns the minimum
-    if (lane == 0) {
-        __stcg(a.gmin + qg, newmin);
-        atomicMax(a.g_best + qg, (uint32_t)(newmin >> 32));
-        if (a.stats) atomicAdd(a.stats + 4, 1ull);
-    }
-}
-
-// Up to 128 exact keys (four per lane, 0 = none) offered to query qg's list in one lock
-// acquisition.  For K <= 128 the list is pulled into registers (4 keys per lane), all
-// candidates are merged there and it is written back once: the lock is held for two L2
-// round trips plus ~30 instructions per surviving candidate.
-// Returns false (nothing done) when `blocking` is off and another CTA holds the lock.
-__device__ __forceinline__ bool list_offer4(const ScanArgs &a, int qg, const uint64_t (&key)[4], bool blocking)
-{
-    const int lane = threadIdx.x & 31;
-    const uint64_t stale = __ldcg(a.gmin + qg);  // may lag behind (smaller): only a pre-filter
-    bool mine = false;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) mine |= (key[r] != 0ull && key[r] > stale);
-    if (!__any_sync(0xffffffffu, mine)) return true;
-    if (blocking) list_lock(a.glock + qg);
-    else if (!list_trylock(a.glock + qg)) return false;
-    const uint64_t fresh = __ldcg(a.gmin + qg);
+    uint64_t *list = c.list + (size_t)ql * a.K;
+    int n = c.lcnt[ql];
     uint32_t cand[4];
-    uint32_t any = 0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        cand[r] = __ballot_sync(0xffffffffu, key[r] != 0ull && key[r] > fresh);
-        any |= cand[r];
-    }
-    if (any && a.K > 128) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            uint32_t c = cand[r];
-            while (c) {
-                const int l = __ffs(c) - 1;
-                c &= c - 1;
-                list_insert_locked(a, qg, __shfl_sync(0xffffffffu, key[r], l));
-                __syncwarp();
-            }
-        }
-    } else if (any) {
-        uint64_t *list = a.glist + (size_t)qg * a.K;
-        int n = __ldcg(a.gcnt + qg);
+    for (int r = 0; r < 4; ++r) cand[r] = __ballot_sync(0xffffffffu, key[r] != 0ull);
+    uint64_t g = 0ull;  // minimum of the full list
+    if (a.K <= 128) {
         uint64_t s[4];  // slot j of lane l <-> list[j * 32 + l]; empty slots hold ~0 (never the minimum)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s[j] = (j * 32 + lane < n) ? __ldcg(list + j * 32 + lane) : ~0ull;
-        unsigned inserted = 0;
-        // current minimum of the (full) list, kept up to date across insertions
-        uint64_t g = 0ull;
-        if (n == a.K) {
+        for (int j = 0; j < 4; ++j) s[j] = (j * 32 + lane < n) ? list[j * 32 + lane] : ~0ull;
+        auto list_min = [&]() {
             uint64_t m = s[0] < s[1] ? s[0] : s[1];
             const uint64_t m23 = s[2] < s[3] ? s[2] : s[3];
-            g = warp_min_u64(m < m23 ? m : m23);
-        }
+            return warp_min_u64(m < m23 ? m : m23);
+        };
+        if (n == a.K) g = list_min();
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            uint32_t c = cand[r];
-            while (c) {
-                const int l = __ffs(c) - 1;
-                c &= c - 1;
+            uint32_t cm = cand[r];
+            while (cm) {
+                const int l = __ffs(cm) - 1;
+                cm &= cm - 1;
                 const uint64_t k = __shfl_sync(0xffffffffu, key[r], l);
                 if (n == a.K && k <= g) continue;
                 const bool dup = (s[0] == k) | (s[1] == k) | (s[2] == k) | (s[3] == k);
@@ -252,61 +158,96 @@ __device__ __forceinline__ bool list_offer4(const ScanArgs &a, int qg, const uin
                     for (int j = 0; j < 4; ++j)
                         if (s[j] == g) s[j] = k;  // keys are unique: one slot of one lane
                 }
-                ++inserted;
-                if (n == a.K) {
-                    uint64_t m = s[0] < s[1] ? s[0] : s[1];
-                    const uint64_t m23 = s[2] < s[3] ? s[2] : s[3];
-                    g = warp_min_u64(m < m23 ? m : m23);
-                }
+                if (n == a.K) g = list_min();
             }
         }
-        if (inserted) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (s[j] != ~0ull) __stcg(list + j * 32 + lane, s[j]);
-            if (lane == 0) {
-                __stcg(a.gcnt + qg, n);
-                if (n == a.K) {
-                    __stcg(a.gmin + qg, g);
-                    atomicMax(a.g_best + qg, (uint32_t)(g >> 32));
-                }
-                if (a.stats) atomicAdd(a.stats + 4, (unsigned long long)inserted);
+        for (int j = 0; j < 4; ++j)
+            if (s[j] != ~0ull) list[j * 32 + lane] = s[j];
+    } else {
+        auto scan_min = [&](uint64_t probe, bool *dup, int *pos) {  // list minimum, its position, and whether probe is present
+            uint64_t m = ~0ull;
+            int p = -1;
+            bool d = false;
+            for (int i = lane; i < n; i += 32) {
+                const uint64_t v = list[i];
+                d |= (v == probe);
+                if (v < m) { m = v; p = i; }
             }
+            const uint64_t gm = warp_min_u64(m);
+            *dup = __any_sync(0xffffffffu, d);
+            const uint32_t owner = __ballot_sync(0xffffffffu, m == gm && p >= 0);
+            *pos = __shfl_sync(0xffffffffu, p, owner ? __ffs(owner) - 1 : 0);
+            return gm;
+        };
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t cm = cand[r];
+            while (cm) {
+                const int l = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const uint64_t k = __shfl_sync(0xffffffffu, key[r], l);
+                if (n == a.K && g != 0ull && k <= g) continue;
+                bool dup;
+                int pos;
+                const uint64_t m = scan_min(k, &dup, &pos);
+                if (dup) continue;
+                if (n < a.K) {
+                    if (lane == 0) list[n] = k;
+                    ++n;
+                    g = 0ull;  // recomputed below / on the next full-list insertion
+                } else if (k > m) {
+                    if (lane == 0) list[pos] = k;
+                    g = 0ull;
+                } else {
+                    g = m;
+                }
+                __syncwarp();
+            }
+        }
+        if (n == a.K && g == 0ull) {
+            bool dup;
+            int pos;
+            g = scan_min(0ull, &dup, &pos);
         }
     }
-    list_unlock(a.glock + qg);
-    return true;
+    __syncwarp();
+    if (lane == 0) c.lcnt[ql] = n;
+    return (n == a.K) ? g : 0ull;
 }
 
 // Settle one query's hit buffer (whole warp): score the pending hits in the reference's
-// arithmetic (four independent load chains per lane) and offer them to the global list;
+// arithmetic (four independent load chains per lane) and merge them into the CTA's list;
 // when the buffer overflowed during this tile, score tile rows [tile_lo, tile_hi)
-// exhaustively instead (nothing is ever lost).
-// With `blocking` off, a buffer of <= 128 hits whose list lock is busy is left untouched and
-// false is returned: the caller moves on to its next query and comes back later.
-__device__ __forceinline__ bool warp_settle(const ScanArgs &a, const QueryCtx &c, int ql, int64_t tile_lo,
-                                            int64_t tile_hi, bool blocking)
+// exhaustively instead (nothing is ever lost).  A full list's minimum is the exact K-th
+// best of the songs this CTA has seen -- a lower bound of the final K-th best -- and is
+// published to every CTA working on the same query (g_best).
+__device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c, int ql, int64_t tile_lo,
+                                            int64_t tile_hi)
 {
     const int lane = threadIdx.x & 31;
     const int raw_cnt = c.cnt[ql];
     const bool overflow = raw_cnt > a.cap;
     const int cnt = overflow ? a.cap : raw_cnt;
-    const int qg = c.qid[ql];
     float q[kF];
 #pragma unroll
     for (int j = 0; j < kF; ++j) q[j] = c.qraw[ql * kF + j];
     const float qn = c.qn[ql];
     const int32_t ex = c.excl[ql];
     const uint32_t *hit = c.hit + (size_t)ql * a.cap;
-    if (overflow || cnt > 128) blocking = true;  // multi-chunk settles never back off
+    // only keys above the current threshold can enter (they are compared again inside the merge)
+    const uint64_t floor_key = (uint64_t)c.best[ql] << 32;
+    uint64_t kth = 0ull;
     for (int base = 0; base < cnt; base += 128) {
         uint64_t key[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int i = base + r * 32 + lane;
             key[r] = (i < cnt) ? exact_key(a, (int64_t)hit[i] - a.id_base, q, qn, ex) : 0ull;
+            if (key[r] < floor_key) key[r] = 0ull;
+            if (key[r]) atomicMax((unsigned long long *)(a.gslot + (size_t)c.qid[ql] * a.K + key_id(key[r]) % (uint32_t)a.K), (unsigned long long)key[r]);
         }
-        if (!list_offer4(a, qg, key, blocking)) return false;
+        kth = list_merge4(a, c, ql, key);
     }
     if (overflow) {
         for (int64_t base = tile_lo; base < tile_hi; base += 128) {
@@ -315,14 +256,32 @@ __device__ __forceinline__ bool warp_settle(const ScanArgs &a, const QueryCtx &c
             for (int r = 0; r < 4; ++r) {
                 const int64_t row = base + r * 32 + lane;
                 key[r] = (row < tile_hi) ? exact_key(a, row, q, qn, ex) : 0ull;
+                if (key[r] < floor_key) key[r] = 0ull;
+                if (key[r]) atomicMax((unsigned long long *)(a.gslot + (size_t)c.qid[ql] * a.K + key_id(key[r]) % (uint32_t)a.K), (unsigned long long)key[r]);
             }
-            list_offer4(a, qg, key, true);
+            kth = list_merge4(a, c, ql, key);
         }
     }
-    __syncwarp();
+    // Global feedback without locks: the K slots hold K distinct songs (distinct residues), so
+    // the smallest slot key is a lower bound of the K-th best over everything ANY CTA has
+    // scored so far -- much tighter than this CTA's own K-th best when many CTAs share a query.
+    uint64_t slot_min = ~0ull;
+    {
+        const uint64_t *slots = a.gslot + (size_t)c.qid[ql] * a.K;
+        for (int i = lane; i < a.K; i += 32) {
+            const uint64_t v = __ldcg(slots + i);
+            slot_min = v < slot_min ? v : slot_min;
+        }
+        slot_min = warp_min_u64(slot_min);  // 0 while some slot is still empty
+    }
     if (lane == 0) {
         c.cnt[ql] = 0;
-        const uint32_t b = __ldcg(a.g_best + qg);
+        uint32_t b = __ldcg(a.g_best + c.qid[ql]);
+        const uint32_t mine = max((uint32_t)(kth >> 32), (uint32_t)(slot_min >> 32));
+        if (mine > b) {
+            atomicMax(a.g_best + c.qid[ql], mine);
+            b = mine;
+        }
         if (b > c.best[ql]) {
             c.best[ql] = b;
             c.nthr[ql] = neg_threshold(b);
@@ -334,7 +293,6 @@ __device__ __forceinline__ bool warp_settle(const ScanArgs &a, const QueryCtx &c
         }
     }
     __syncwarp();
-    return true;
 }
 
 // Layout of the normalised store for a kernel shape (S songs per thread, THREADS per CTA):
@@ -381,12 +339,14 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     QueryCtx c;
-    c.qraw = reinterpret_cast<float *>(smem_raw);
+    c.list = reinterpret_cast<uint64_t *>(smem_raw);
+    c.qraw = reinterpret_cast<float *>(c.list + (size_t)a.qt * a.K);
     c.nthr = c.qraw + a.qt * kF;
     c.qn = c.nthr + a.qt;
     c.best = reinterpret_cast<uint32_t *>(c.qn + a.qt);
     c.cnt = reinterpret_cast<int *>(c.best + a.qt);
-    c.excl = c.cnt + a.qt;
+    c.lcnt = c.cnt + a.qt;
+    c.excl = c.lcnt + a.qt;
     c.qid = c.excl + a.qt;
     c.hit = reinterpret_cast<uint32_t *>(c.qid + a.qt);
     // s_flag[tile % 3] != 0: some hit buffer filled up during that tile (set by the appending
@@ -418,6 +378,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             c.qid[ql] = qid;
             c.excl[ql] = a.exclude[qid];
             c.cnt[ql] = 0;
+            c.lcnt[ql] = 0;
             c.qn[ql] = a.qn[qid];
             const uint32_t b = __ldcg(a.g_best + qid);
             c.best[ql] = b;
@@ -447,12 +408,8 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             }
 
             // a settle phase follows this tile if some hit buffer fills up (flagged by the thread
-            // whose append crosses the mark), and always after a segment's first and last tile
-            // every CTA settles everything after its last tile; one CTA in force_mod (about eight
-            // per query tile) also after its first tile, which is enough to fill the lists and
-            // publish selective thresholds early without every CTA of a query tile queueing on
-            // the same list locks
-            const bool forced = (tile == t1 - 1) || (tile == t0 && (int)(blockIdx.x % (unsigned)a.force_mod) == 0);
+            // whose append crosses the mark), and always after the last tile of the segment
+            const bool forced = (tile == t1 - 1);
             // thresholds other CTAs published meanwhile: requested now, consumed after the hot loop
             uint32_t g_pre = 0;
             if (warp + WARPS * lane < nql) g_pre = __ldcg(a.g_best + c.qid[warp + WARPS * lane]);
@@ -537,26 +494,27 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 uint32_t todo = __ballot_sync(0xffffffffu, need);
                 const int64_t tile_lo = stile * TS;
                 const int64_t tile_hi = min(a.n, tile_lo + TS);
-                // each CTA starts at a different one of its warp's queries, so the CTAs sharing a
-                // query tile do not convoy through the same sequence of list locks
-                const int per_warp = (nql + WARPS - 1) / WARPS;
-                const int rot = (int)(blockIdx.x % (unsigned)per_warp);
-                const uint32_t lo_mask = (1u << rot) - 1u;
-                uint32_t first = todo & ~lo_mask, second = todo & lo_mask, retry = 0;
-                while (first | second) {  // first round: skip queries whose list is locked by another CTA
-                    uint32_t &w = first ? first : second;
-                    const int l = __ffs(w) - 1;
-                    w &= w - 1;
-                    if (!warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi, false)) retry |= 1u << l;
-                }
-                while (retry) {  // second round: wait for them
-                    const int l = __ffs(retry) - 1;
-                    retry &= retry - 1;
-                    warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi, true);
+                while (todo) {
+                    const int l = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi);
                 }
                 __syncthreads();
             }
         }
+        // ---- segment epilogue: hand this CTA's exact survivors to the per-query pool
+        // (the last tile's settle phase and its closing barrier have just run)
+        for (int ql = warp; ql < nql; ql += WARPS) {
+            const int n = c.lcnt[ql];
+            if (n == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(a.pool_cnt + q0 + ql, n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            uint64_t *slab = a.pool + (size_t)(q0 + ql) * a.segs * a.K;
+            const uint64_t *list = c.list + (size_t)ql * a.K;
+            for (int i = lane; i < n; i += 32) slab[base + i] = list[i];
+        }
+        __syncthreads();
         u += (t1 - t0);
         t0 = 0;
         ++qtile;
