@@ -231,7 +231,7 @@ def run_ours(args) -> None:
     clocks = sampler.stop(t_wall0, t_wall1)
     launches = eng.stat("kernel_launches")
     scan_ms, scan_n = eng.timing("scan")
-    other = {k: eng.timing(k)[0] / args.steps for k in ("prep", "sample", "finalize", "merge")}
+    other = {k: eng.timing(k)[0] / args.steps for k in ("prep", "sample", "bound", "finalize", "merge")}
     eng.set_option("profile", 0)
     checksum = int(out_i.to(torch.int64).sum().item())  # the step's result is really read
 

@@ -113,22 +113,26 @@ int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k,
                              int32_t *out_idx, float *out_score);
 
 /* Tunables (DESIGN.md "knobs"):
- *   "variant"   scan kernel shape, index into the table sr_engine_variant_name() lists
- *   "qt"        queries per shared-memory tile (1..128)
+ *   "variant"   scan kernel shape, index into the table sr_engine_variant_name() lists;
+ *               -1 (default) picks by batch size
+ *   "qt"        queries per shared-memory tile (1..256)
  *   "batch"     max queries per internal pass (workspace is sized for it)
  *   "sample"    threshold-bootstrap sample size per query (0 = off, else power of two <= 4096)
+ *   "hit_cap"   hit-buffer entries per query per CTA (multiple of 32; 0 = sized from k)
+ *   "settle_at" hits after which a query's buffer is scored and merged (0 = hit_cap / 4)
+ *   "bound"     0: skip the bound pass (threshold bootstrap at filter speed)
  *   "profile"   1: bracket every kernel with CUDA events (read with sr_engine_get_timing)
  *   "reset"     any value: zero the counters and timings below               */
 int sr_engine_set_option(sr_engine *e, const char *key, int64_t value);
 
 /* Counters since create()/reset (synchronises the engine's stream):
- * "kernel_launches", "queries", "filter_hits", "settles", "rescans", "rescored",
+ * "kernel_launches", "queries", "filter_hits", "settles", "rescans", "refilters", "rescored",
  * "irregular_songs", "sm_count", "scan_grid", "scan_tile_songs", "device_bytes",
- * "variant", "qt". */
+ * "variant" (the shape the last pass used), "qt". */
 int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value);
 
 /* With "profile" on: total device milliseconds and launch count of one kernel
- * ("prep", "sample", "scan", "finalize", "merge") since the last reset, measured
+ * ("prep", "sample", "bound", "scan", "finalize", "merge") since the last reset, measured
  * with CUDA events on the launching stream.  Synchronises that stream. */
 int sr_engine_get_timing(sr_engine *e, const char *kernel, double *ms_total, int64_t *launches);
 

@@ -13,13 +13,13 @@ namespace sr {
 // hat  : row / ||row|| computed in double and rounded once; +NaN for irregular rows
 //        (norm not 0 and outside [kNormLo,kNormHi], or not finite): those always pass
 //        the scan filter and are therefore always scored exactly.
-//        laid out for the scan kernel shape (S, THREADS): see hat_offset() in sr_scan.cuh
-__global__ void build_store_kernel(const float *raw, int64_t n, int64_t n_pad, float *nf, float *hat, int S, int THREADS,
+//        laid out for S songs per thread: see hat_offset() in sr_scan.cuh
+__global__ void build_store_kernel(const float *raw, int64_t n, int64_t n_pad, float *nf, float *hat, int S,
                                    unsigned long long *n_irregular)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
-    float *hp = hat + hat_offset(i, 0, S, THREADS);  // feature j lives at hp[2 * j]
+    float *hp = hat + hat_offset(i, 0, S);  // feature j lives at hp[2 * j]
     if (i >= n) {
         nf[i] = 0.0f;
 #pragma unroll

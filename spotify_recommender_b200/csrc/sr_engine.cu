@@ -66,15 +66,13 @@ const Variant kVariants[] = {
     SR_VARIANT(8, 256, 2, true),
     SR_VARIANT(8, 512, 1, false),
     SR_VARIANT(8, 512, 1, true),
-    SR_VARIANT(8, 384, 1, false),
-    SR_VARIANT(8, 384, 1, true),
     SR_VARIANT(4, 256, 4, true),
-    SR_VARIANT(12, 384, 1, true),
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+constexpr int kAutoSmall = 1, kAutoLarge = 3, kAutoS = 8;
 
-enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kPilot, kBound, kNumKernels };
-const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge", "pilot", "bound"};
+enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kBound, kNumKernels };
+const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge", "bound"};
 
 struct DevBuf {
     void *p = nullptr;
@@ -94,17 +92,17 @@ struct sr_engine {
     int64_t n = 0, n_pad = 0;
     int32_t id_base = 0;
     int64_t irregular = 0;
-    int hat_variant = -1;  // kernel shape d_hat is laid out for
+    int hat_S = -1;  // songs per thread d_hat is laid out for
+    int last_variant = kAutoLarge;
 
     // options
-    int variant = 3;
+    int variant = -1;  // -1: chosen per pass by batch size (same store layout for every S = 8 shape)
     int qt_opt = kQTMax;
     int batch = 8192;
     int sample = -1;  // -1: automatic
-    bool pilot = false; // pilot passes before the full scan
     bool bound = true;  // bound pass (filter-speed threshold bootstrap)
     int settle_at = 0;  // 0: hit_cap / 4
-    int hit_cap = 128; // hit-buffer entries per query in shared memory
+    int hit_cap = 0;   // hit-buffer entries per query in shared memory (0: sized from K)
     bool profile = false;
 
     // batch workspace (grow-only)
@@ -123,8 +121,8 @@ struct sr_engine {
         int kernel;
     };
     std::vector<Timed> pending;
-    double ms_total[kNumKernels] = {0, 0, 0, 0, 0, 0, 0};
-    int64_t ms_count[kNumKernels] = {0, 0, 0, 0, 0, 0, 0};
+    double ms_total[kNumKernels] = {0, 0, 0, 0, 0, 0};
+    int64_t ms_count[kNumKernels] = {0, 0, 0, 0, 0, 0};
     int64_t device_bytes = 0;
 };
 
@@ -230,9 +228,9 @@ int build_store(sr_engine *e)
     const int threads = 256;
     const int64_t blocks = (e->n_pad + threads - 1) / threads;
     build_store_kernel<<<(unsigned)blocks, threads, 0, e->stream>>>(e->d_raw, e->n, e->n_pad, e->d_nf, e->d_hat,
-                                                                     kVariants[e->variant].S, kVariants[e->variant].threads,
+                                                                     e->variant >= 0 ? kVariants[e->variant].S : kAutoS,
                                                                      e->d_irregular);
-    e->hat_variant = e->variant;
+    e->hat_S = e->variant >= 0 ? kVariants[e->variant].S : kAutoS;
     SR_CUDA(cudaGetLastError());
     ++e->launches;
     unsigned long long irr = 0;
@@ -277,22 +275,33 @@ cudaEvent_t g_bank_event[64] = {nullptr};
 int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const int32_t *d_excl, int nq, int K,
              int32_t *d_out_idx, float *d_out_score, cudaStream_t st)
 {
-    const Variant &v = kVariants[e->variant];
+    // small batches are HBM-bound: two 256-thread CTAs per SM overlap one CTA's tile load with
+    // the other's arithmetic; large batches are FP32-bound: one 512-thread CTA, bigger tiles
+    const int vi = e->variant >= 0 ? e->variant : (nq <= 48 ? kAutoSmall : kAutoLarge);
+    e->last_variant = vi;
+    const Variant &v = kVariants[vi];
     const int TS = v.S * v.threads;
     const int n_tiles = (int)((e->n + TS - 1) / TS);
     // query groups (what fits the constant bank), evenly filled; then query tiles inside a group
     const int groups = (nq + kConstQueries - 1) / kConstQueries;
     const int gsize = (nq + groups - 1) / groups;
-    // queries per tile and hit-buffer size: as large as asked for and as fits in shared memory
-    // next to the CTA's exact top-K lists (qt x K keys)
-    int qt_cap = std::max(1, std::min(e->qt_opt, kQTMax));
-    int cap = e->hit_cap;
-    const size_t smem_budget = (size_t)200 * 1024 / v.ctas;
-    while (scan_smem_bytes(qt_cap, cap, K) > smem_budget) {
-        if (cap > 32) cap /= 2;
-        else if (qt_cap > 8) qt_cap /= 2;
-        else return fail(e, SR_EINVAL, "k = %d does not fit the scan kernel's shared memory", K);
+    // Queries per tile (qt) and hit-buffer entries per query (cap), both in shared memory next to
+    // the CTA's exact top-K lists (qt x K keys).  Large qt amortises the per-tile costs; cap of a
+    // few K lets an overflowing buffer alone lift the threshold far enough for the re-filter
+    // round to converge.  First combination that fits wins.
+    const size_t smem_budget = (size_t)216 * 1024 / v.ctas;
+    const int qt_max = std::max(1, std::min(e->qt_opt, kQTMax));
+    const int kk = std::max(K, 32);
+    int qt_cap = 0, cap = 0;
+    for (int qtry = qt_max; qtry >= 1 && !qt_cap; qtry = (qtry > 8 ? qtry / 2 : qtry - 1)) {
+        const int caps[4] = {e->hit_cap > 0 ? e->hit_cap : std::max(128, 4 * kk), std::max(128, 2 * kk),
+                             std::max(128, 3 * kk / 2), qtry <= 64 ? std::max(32, kk) : 0};
+        for (int ci = 0; ci < 4 && !qt_cap; ++ci) {
+            const int ctry = std::min(1024, (caps[ci] + 31) / 32 * 32);
+            if (ctry > 0 && scan_smem_bytes(qtry, ctry, K) <= smem_budget) { qt_cap = qtry; cap = ctry; }
+        }
     }
+    if (!qt_cap) return fail(e, SR_EINVAL, "k = %d does not fit the scan kernel's shared memory", K);
     const int nqt0 = (gsize + qt_cap - 1) / qt_cap;
     const int qt = (gsize + nqt0 - 1) / nqt0;
     const int nqt = (gsize + qt - 1) / qt;
@@ -388,21 +397,14 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             SR_CUDA(cudaGetLastError());
             ++e->launches;
         }
-        // Pilot passes: the same kernel over 8, then 64 evenly spaced song tiles first.  They cost
-        // < 2 % of the work and leave every query with the exact top-K of a 10^4..10^5-song sample,
-        // so the full pass starts with a selective threshold on every CTA at once (the full pass
-        // meets the pilot tiles again; list insertion ignores duplicates).
-        const int passes[3] = {e->pilot ? 8 : 0, e->pilot ? 64 : 0, n_tiles};
-        for (int pi = 0; pi < 3; ++pi) {
-            const int pt = passes[pi];
-            if (pt <= 0 || (pi < 2 && n_tiles < 8 * pt)) continue;
-            a.n_tiles = pt;
-            a.tile_stride = (pi < 2) ? n_tiles / pt : 1;
-            const int64_t gunits = (int64_t)gnqt * pt;
+        {
+            a.n_tiles = n_tiles;
+            a.tile_stride = 1;
+            const int64_t gunits = (int64_t)gnqt * n_tiles;
             const int ggrid = (int)std::min<int64_t>(grid, gunits);
             a.upc = (int)(gunits / ggrid);
             a.extra = (int)(gunits % ggrid);
-            Scope sc(e, st, pi < 2 ? kPilot : kScan);
+            Scope sc(e, st, kScan);
             SR_CUDA(v.launch(a, ggrid, smem, st));
         }
         SR_CUDA(cudaEventRecord(ev, st));
@@ -684,9 +686,9 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
 {
     if (!e || !key) return SR_EINVAL;
     if (!strcmp(key, "variant")) {
-        if (value < 0 || value >= kNumVariants) return fail(e, SR_EINVAL, "variant must be in [0, %d)", kNumVariants);
+        if (value < -1 || value >= kNumVariants) return fail(e, SR_EINVAL, "variant must be -1 (auto) or in [0, %d)", kNumVariants);
         e->variant = (int)value;
-        if (e->d_raw && e->hat_variant != e->variant) {  // the normalised store is laid out per kernel shape
+        if (e->d_raw && e->hat_S != (e->variant >= 0 ? kVariants[e->variant].S : kAutoS)) {  // the normalised store is laid out per S
             SR_CUDA(cudaSetDevice(e->device));
             SR_CUDA(cudaStreamSynchronize(e->stream));
             int rc = build_store(e);
@@ -707,10 +709,8 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
         e->settle_at = (int)value;
     } else if (!strcmp(key, "bound")) {
         e->bound = value != 0;
-    } else if (!strcmp(key, "pilot")) {
-        e->pilot = value != 0;
     } else if (!strcmp(key, "hit_cap")) {
-        if (value < 32 || value > 1024 || value % 32) return fail(e, SR_EINVAL, "hit_cap must be a multiple of 32 in [32, 1024]");
+        if (value != 0 && (value < 32 || value > 1024 || value % 32)) return fail(e, SR_EINVAL, "hit_cap must be 0 (auto) or a multiple of 32 in [32, 1024]");
         e->hit_cap = (int)value;
     } else if (!strcmp(key, "profile")) {
         e->profile = value != 0;
@@ -732,7 +732,7 @@ int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value)
 {
     if (!e || !key || !value) return SR_EINVAL;
     SR_CUDA(cudaSetDevice(e->device));
-    static const char *const dev_keys[] = {"filter_hits", "settles", "rescans", "rescored", "inserts"};
+    static const char *const dev_keys[] = {"filter_hits", "settles", "rescans", "rescored", "refilters"};
     for (int i = 0; i < 5; ++i) {
         if (!strcmp(key, dev_keys[i])) {
             unsigned long long h[8];
@@ -747,9 +747,9 @@ int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value)
     else if (!strcmp(key, "irregular_songs")) *value = e->irregular;
     else if (!strcmp(key, "sm_count")) *value = e->sm_count;
     else if (!strcmp(key, "scan_grid")) *value = e->scan_grid;
-    else if (!strcmp(key, "scan_tile_songs")) *value = kVariants[e->variant].S * kVariants[e->variant].threads;
+    else if (!strcmp(key, "scan_tile_songs")) *value = kVariants[e->last_variant].S * kVariants[e->last_variant].threads;
     else if (!strcmp(key, "device_bytes")) *value = e->device_bytes;
-    else if (!strcmp(key, "variant")) *value = e->variant;
+    else if (!strcmp(key, "variant")) *value = e->last_variant;
     else if (!strcmp(key, "qt")) *value = e->qt_opt;
     else return fail(e, SR_EINVAL, "unknown stat '%s'", key);
     return SR_OK;

@@ -70,7 +70,7 @@ struct ScanArgs {
 
 __host__ __device__ inline size_t scan_smem_bytes(int qt, int cap, int K)
 {
-    return (size_t)qt * K * 8 + (size_t)qt * (kF + 7 + cap) * 4 + 16;
+    return (size_t)qt * K * 8 + (size_t)qt * (kF + 9 + cap) * 4 + 32;
 }
 
 // CTA runs (segments) that can touch one query tile = slab capacity of the pool, in lists:
@@ -222,8 +222,12 @@ __device__ __forceinline__ uint64_t list_merge4(const ScanArgs &a, const QueryCt
 // exhaustively instead (nothing is ever lost).  A full list's minimum is the exact K-th
 // best of the songs this CTA has seen -- a lower bound of the final K-th best -- and is
 // published to every CTA working on the same query (g_best).
+// An overflowed buffer (more than `cap` hits in this tile) is handled in two ways: normally
+// the buffered hits alone raise the threshold (they contain >= cap candidates), the query is
+// put on `redo` and the whole CTA re-filters the tile -- still in registers -- against the
+// raised threshold; if the threshold did not move (mass ties) the tile is scored exhaustively.
 __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c, int ql, int64_t tile_lo,
-                                            int64_t tile_hi)
+                                            int64_t tile_hi, int *redo, int *redo_cnt)
 {
     const int lane = threadIdx.x & 31;
     const int raw_cnt = c.cnt[ql];
@@ -236,7 +240,8 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
     const int32_t ex = c.excl[ql];
     const uint32_t *hit = c.hit + (size_t)ql * a.cap;
     // only keys above the current threshold can enter (they are compared again inside the merge)
-    const uint64_t floor_key = (uint64_t)c.best[ql] << 32;
+    const uint32_t best_before = c.best[ql];
+    const uint64_t floor_key = (uint64_t)best_before << 32;
     uint64_t kth = 0ull;
     for (int base = 0; base < cnt; base += 128) {
         uint64_t key[4];
@@ -249,58 +254,73 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
         }
         kth = list_merge4(a, c, ql, key);
     }
-    if (overflow) {
-        for (int64_t base = tile_lo; base < tile_hi; base += 128) {
-            uint64_t key[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int64_t row = base + r * 32 + lane;
-                key[r] = (row < tile_hi) ? exact_key(a, row, q, qn, ex) : 0ull;
-                if (key[r] < floor_key) key[r] = 0ull;
-                if (key[r]) atomicMax((unsigned long long *)(a.gslot + (size_t)c.qid[ql] * a.K + key_id(key[r]) % (uint32_t)a.K), (unsigned long long)key[r]);
-            }
-            kth = list_merge4(a, c, ql, key);
-        }
-    }
-    // Global feedback without locks: the K slots hold K distinct songs (distinct residues), so
-    // the smallest slot key is a lower bound of the K-th best over everything ANY CTA has
-    // scored so far -- much tighter than this CTA's own K-th best when many CTAs share a query.
-    uint64_t slot_min = ~0ull;
-    {
+    // A full list's minimum is this CTA's exact K-th best.  Global feedback without locks: the
+    // K residue slots hold K distinct songs, so the smallest slot key is a lower bound of the
+    // K-th best over everything ANY CTA has scored so far -- much tighter than this CTA's own
+    // K-th best when many CTAs share a query.  The better of the two is published.
+    auto publish = [&](uint64_t kth_key) {
+        uint64_t slot_min = ~0ull;
         const uint64_t *slots = a.gslot + (size_t)c.qid[ql] * a.K;
         for (int i = lane; i < a.K; i += 32) {
             const uint64_t v = __ldcg(slots + i);
             slot_min = v < slot_min ? v : slot_min;
         }
         slot_min = warp_min_u64(slot_min);  // 0 while some slot is still empty
+        if (lane == 0) {
+            uint32_t b = __ldcg(a.g_best + c.qid[ql]);
+            const uint32_t mine = max((uint32_t)(kth_key >> 32), (uint32_t)(slot_min >> 32));
+            if (mine > b) {
+                atomicMax(a.g_best + c.qid[ql], mine);
+                b = mine;
+            }
+            if (b > c.best[ql]) {
+                c.best[ql] = b;
+                c.nthr[ql] = neg_threshold(b);
+            }
+        }
+        __syncwarp();
+    };
+    publish(kth);
+    bool rescanned = false;
+    if (overflow) {
+        if (c.best[ql] > best_before) {
+            if (lane == 0) redo[atomicAdd(redo_cnt, 1)] = ql;  // re-filter the tile against the raised threshold
+        } else {
+            rescanned = true;
+            for (int64_t base = tile_lo; base < tile_hi; base += 128) {
+                uint64_t key[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int64_t row = base + r * 32 + lane;
+                    key[r] = (row < tile_hi) ? exact_key(a, row, q, qn, ex) : 0ull;
+                    if (key[r] < floor_key) key[r] = 0ull;
+                    if (key[r]) atomicMax((unsigned long long *)(a.gslot + (size_t)c.qid[ql] * a.K + key_id(key[r]) % (uint32_t)a.K), (unsigned long long)key[r]);
+                }
+                kth = list_merge4(a, c, ql, key);
+            }
+            publish(kth);
+        }
     }
     if (lane == 0) {
         c.cnt[ql] = 0;
-        uint32_t b = __ldcg(a.g_best + c.qid[ql]);
-        const uint32_t mine = max((uint32_t)(kth >> 32), (uint32_t)(slot_min >> 32));
-        if (mine > b) {
-            atomicMax(a.g_best + c.qid[ql], mine);
-            b = mine;
-        }
-        if (b > c.best[ql]) {
-            c.best[ql] = b;
-            c.nthr[ql] = neg_threshold(b);
-        }
         if (a.stats) {
             atomicAdd(a.stats + 1, 1ull);
-            if (overflow) atomicAdd(a.stats + 2, 1ull);
-            atomicAdd(a.stats + 3, (unsigned long long)(cnt + (overflow ? (tile_hi - tile_lo) : 0)));
+            if (rescanned) atomicAdd(a.stats + 2, 1ull);
+            if (overflow && !rescanned) atomicAdd(a.stats + 4, 1ull);
+            atomicAdd(a.stats + 3, (unsigned long long)(cnt + (rescanned ? (tile_hi - tile_lo) : 0)));
         }
     }
     __syncwarp();
 }
 
-// Layout of the normalised store for a kernel shape (S songs per thread, THREADS per CTA):
-// a tile holds TS = S*THREADS consecutive songs; thread t owns songs t + s*THREADS and
-// multiplies them in pairs (2p, 2p+1).  The two songs of a pair are stored interleaved,
+// Layout of the normalised store (S songs per thread, kLT = 256 "layout threads"): a layout
+// tile holds S*kLT consecutive songs; layout thread t owns songs t + s*kLT and multiplies them
+// in pairs (2p, 2p+1).  A CTA of THREADS = m*kLT threads works on m consecutive layout tiles
+// (its tile), so every kernel shape with the same S reads the same store.  The two songs of a pair are stored interleaved,
 // [a0 b0 a1 b1 ... a11 b11], so one 128-bit load yields two ready FFMA2 operands and a
 // warp's loads cover a contiguous 3 KB.  Float offset of feature j of local row `row`:
-__host__ __device__ __forceinline__ int64_t hat_offset(int64_t row, int j, int S, int THREADS)
+constexpr int kLT = 256;
+__host__ __device__ __forceinline__ int64_t hat_offset(int64_t row, int j, int S, int THREADS = kLT)
 {
     const int64_t TS = (int64_t)S * THREADS;
     const int64_t tile = row / TS;
@@ -333,6 +353,8 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 {
     constexpr int TS = S * THREADS;
     constexpr int WARPS = THREADS / 32;
+    constexpr int SUB = THREADS / kLT;  // layout tiles per CTA tile
+    static_assert(THREADS % kLT == 0, "CTA size must be a multiple of the layout tile's thread count");
     static_assert(S % 2 == 0, "songs per thread must be even");
     static_assert(kQTMax <= 32 * WARPS, "one lane per owned query in the tile epilogue");
     static_assert(kRowPad % TS == 0, "store padding must cover whole tiles");
@@ -354,7 +376,10 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     // read right after tile t's barrier, cleared after tile t+1's barrier (every read is done),
     // and next written during tile t+3, which starts after tile t+2's barrier.
     int *s_flag = reinterpret_cast<int *>(c.hit + (size_t)a.qt * a.cap);
+    int *s_redo_cnt = s_flag + 4;                 // [2]
+    int *s_redo = s_redo_cnt + 4;                 // [2][qt] queries whose tile must be re-filtered
     if (threadIdx.x < 3) s_flag[threadIdx.x] = 0;
+    if (threadIdx.x < 2) s_redo_cnt[threadIdx.x] = 0;
     int tphase = 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -389,18 +414,19 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 
         for (int tile = t0; tile < t1; ++tile) {
             const int64_t stile = (int64_t)tile * a.tile_stride;  // store tile
-            const int64_t row0 = stile * TS + tid;
+            const int64_t ltile = stile * SUB + tid / kLT;      // this thread's layout tile
+            const int64_t row0 = ltile * (S * kLT) + tid % kLT;  // its songs: row0 + s * kLT
 
             // ---- S songs of the normalised store into registers: S/2 interleaved pairs,
             // six 128-bit loads each, every load two ready FFMA2 operands
             float2 fp[S / 2][kF];
             {
-                const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (stile * (S / 2) * THREADS + tid) * 6;
+                const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (ltile * (S / 2) * kLT + tid % kLT) * 6;
 #pragma unroll
                 for (int p = 0; p < S / 2; ++p) {
 #pragma unroll
                     for (int c4 = 0; c4 < 6; ++c4) {
-                        const float4 v = __ldg(src + (int64_t)p * THREADS * 6 + c4);
+                        const float4 v = __ldg(src + (int64_t)p * kLT * 6 + c4);
                         fp[p][2 * c4] = make_float2(v.x, v.y);
                         fp[p][2 * c4 + 1] = make_float2(v.z, v.w);
                     }
@@ -421,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     for (int h = 0; h < 2; ++h) {
                         const float v = h ? acc[p].y : acc[p].x;
                         if ((int)__float_as_uint(v) >= 0) {
-                            const int64_t row = row0 + (int64_t)(2 * p + h) * THREADS;
+                            const int64_t row = row0 + (int64_t)(2 * p + h) * kLT;
                             if (row < a.n) {
                                 const int slot = atomicAdd(&c.cnt[ql], 1);
                                 if (slot < a.cap) c.hit[(size_t)ql * a.cap + slot] = (uint32_t)(a.id_base + (int32_t)row);
@@ -497,9 +523,44 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 while (todo) {
                     const int l = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi);
+                    warp_settle(a, c, warp + WARPS * l, tile_lo, tile_hi, s_redo, s_redo_cnt);
                 }
                 __syncthreads();
+                // re-filter rounds for queries whose buffer overflowed: the tile is still in
+                // registers, one filter iteration per flagged query against the raised threshold
+                for (int rp = 0;; rp ^= 1) {
+                    const int nr = s_redo_cnt[rp];
+                    if (nr == 0) break;
+                    const int *list = s_redo + rp * a.qt;
+                    {
+                        // the tile is re-read (L2-hot) rather than kept alive in registers across
+                        // the settle code, which would spill
+                        float2 fr[S / 2][kF];
+                        const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (ltile * (S / 2) * kLT + tid % kLT) * 6;
+#pragma unroll
+                        for (int p = 0; p < S / 2; ++p) {
+#pragma unroll
+                            for (int c4 = 0; c4 < 6; ++c4) {
+                                const float4 v = __ldcg(src + (int64_t)p * kLT * 6 + c4);
+                                fr[p][2 * c4] = make_float2(v.x, v.y);
+                                fr[p][2 * c4 + 1] = make_float2(v.z, v.w);
+                            }
+                        }
+                        for (int r = 0; r < nr; ++r) {
+                            const int ql = list[r];
+                            float2 acc[S / 2];
+                            const uint32_t m = filter_query<S>(fr, q0 + ql, c.nthr[ql], acc);
+                            if ((int)m >= 0) append(ql, acc);
+                        }
+                    }
+                    __syncthreads();
+                    if (tid == 0) s_redo_cnt[rp] = 0;
+                    for (int r = 0; r < nr; ++r) {
+                        const int ql = list[r];
+                        if (ql % WARPS == warp) warp_settle(a, c, ql, tile_lo, tile_hi, s_redo + (rp ^ 1) * a.qt, s_redo_cnt + (rp ^ 1));
+                    }
+                    __syncthreads();
+                }
             }
         }
         // ---- segment epilogue: hand this CTA's exact survivors to the per-query pool
@@ -544,15 +605,15 @@ __global__ void __launch_bounds__(THREADS, MINB) bound_kernel(const ScanArgs a, 
         const int nql = min(a.qt, a.nq - q0);
         for (int i = tid; i < nql; i += THREADS) s_max[i] = kOrdNegInf;
         __syncthreads();
-        const int64_t stile = (int64_t)j * stride;
+        const int64_t ltile = (int64_t)j * stride * (THREADS / kLT) + tid / kLT;
         float2 fp[S / 2][kF];
         {
-            const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (stile * (S / 2) * THREADS + tid) * 6;
+            const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (ltile * (S / 2) * kLT + tid % kLT) * 6;
 #pragma unroll
             for (int p = 0; p < S / 2; ++p) {
 #pragma unroll
                 for (int c4 = 0; c4 < 6; ++c4) {
-                    const float4 v = __ldg(src + (int64_t)p * THREADS * 6 + c4);
+                    const float4 v = __ldg(src + (int64_t)p * kLT * 6 + c4);
                     fp[p][2 * c4] = make_float2(v.x, v.y);
                     fp[p][2 * c4 + 1] = make_float2(v.z, v.w);
                 }
