@@ -66,7 +66,7 @@ struct PrepArgs {
     float *qraw, *qn, *qhat;  // outputs
     int32_t *excl;
     int32_t *pool_cnt;        // per-query state, reset here
-    uint32_t *g_best, *gbound;
+    uint32_t *g_best;
     int32_t *bad_index;       // set to 1 when a gather id is not owned by this store
 };
 
@@ -111,7 +111,6 @@ __global__ void prep_queries_kernel(const PrepArgs a)
     }
     a.pool_cnt[q] = 0;
     a.g_best[q] = kOrdNegInf;
-    a.gbound[q] = 0xFFFFFFFFu;  // min-reduced by the bound pass
 }
 
 // ---- threshold bootstrap (stores too small for the bound pass) -----------------------------

@@ -25,7 +25,8 @@ thread_local std::string g_create_error;
 // ---- scan kernel shapes --------------------------------------------------------
 typedef cudaError_t (*ScanLaunch)(const ScanArgs &, int grid, size_t smem, cudaStream_t st);
 typedef cudaError_t (*ScanOcc)(int *ctas_per_sm, size_t smem);
-typedef cudaError_t (*BoundLaunch)(const ScanArgs &, int nb, int stride, int grid, size_t smem, cudaStream_t st);
+typedef cudaError_t (*BoundLaunch)(const ScanArgs &, int nblk, int n_sample, int stride, uint32_t *gmax, int grid, size_t smem,
+                                   cudaStream_t st);
 
 template <int S, int T, int M, bool D>
 cudaError_t launch_scan(const ScanArgs &a, int grid, size_t smem, cudaStream_t st)
@@ -46,9 +47,13 @@ cudaError_t occ_scan(int *ctas, size_t smem)
 }
 
 template <int S, int T, int M>
-cudaError_t launch_bound(const ScanArgs &a, int nb, int stride, int grid, size_t smem, cudaStream_t st)
+cudaError_t launch_bound(const ScanArgs &a, int nblk, int n_sample, int stride, uint32_t *gmax, int grid, size_t smem,
+                         cudaStream_t st)
 {
-    bound_kernel<S, T, M><<<grid, T, smem, st>>>(a, nb, stride);
+    auto k = bound_kernel<S, T, M>;
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k<<<grid, T, smem, st>>>(a, nblk, n_sample, stride, gmax);
     return cudaGetLastError();
 }
 
@@ -320,25 +325,33 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     }
     const int segs = scan_segs(n_tiles, upc_min);
 
+    // threshold bootstrap: the bound pass (filter speed, per query group) when the store has
+    // enough full tiles, else the exact sample
+    const int64_t full_tiles = e->n / TS;
+    const int nblk = K + 1;                                  // disjoint blocks of sample songs
+    const int n_sample = (int)std::min<int64_t>(128 / (v.threads / kLT), full_tiles / 4);  // sample tiles (128 layout tiles)
+    const bool use_bound = e->bound && nblk <= kLT / 2 && n_sample >= 4 && (int64_t)n_sample * TS >= 64 * (int64_t)nblk;
+
     int rc;
     if ((rc = ensure(e, e->qraw, (size_t)nq * kF * 4))) return rc;
     if ((rc = ensure(e, e->qn, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->qhat, (size_t)nq * kF * 4))) return rc;
     if ((rc = ensure(e, e->excl, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gbest, (size_t)nq * 4))) return rc;
-    if ((rc = ensure(e, e->gbound, (size_t)nq * 4))) return rc;
+    if ((rc = ensure(e, e->gbound, (size_t)nq * nblk * 4))) return rc;
     if ((rc = ensure(e, e->gslot, (size_t)nq * K * 8))) return rc;
     if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->pool, (size_t)nq * segs * K * 8))) return rc;
 
     SR_CUDA(cudaMemsetAsync(e->gslot.p, 0, (size_t)nq * K * 8, st));
+    if (use_bound) SR_CUDA(cudaMemsetAsync(e->gbound.p, 0, (size_t)nq * nblk * 4, st));
     {
         PrepArgs p;
         p.raw_store = e->d_raw; p.n = e->n; p.id_base = e->id_base;
         p.qidx = d_qidx; p.qrows_in = d_qrows; p.excl_in = d_excl; p.nq = nq;
         p.qraw = (float *)e->qraw.p; p.qn = (float *)e->qn.p; p.qhat = (float *)e->qhat.p;
         p.excl = (int32_t *)e->excl.p; p.pool_cnt = (int32_t *)e->pool_cnt.p;
-        p.g_best = (uint32_t *)e->gbest.p; p.gbound = (uint32_t *)e->gbound.p;
+        p.g_best = (uint32_t *)e->gbest.p;
         p.bad_index = e->d_flag;
         Scope sc(e, st, kPrep);
         prep_queries_kernel<<<(nq + 127) / 128, 128, 0, st>>>(p);
@@ -346,9 +359,6 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     }
     // threshold bootstrap: the bound pass (filter speed, per query group, below) when the store
     // has enough full tiles, else / additionally the exact sample
-    const int64_t full_tiles = e->n / TS;
-    const int nb = K + 1;
-    const bool use_bound = e->bound && full_tiles >= 4 * (int64_t)nb;
     int m = e->sample;
     if (m < 0 && use_bound) m = 0;
     if (m < 0) m = std::min(kSortCap, std::max(1024, 2 * pow2_floor((int64_t)K * 32 - 1)));
@@ -376,7 +386,6 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.pool = (uint64_t *)e->pool.p + (size_t)g0 * segs * K; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
         a.segs = segs;
         a.g_best = (uint32_t *)e->gbest.p + g0;
-        a.gbound = (uint32_t *)e->gbound.p + g0;
         a.stats = e->d_stats;
         const int gnqt = (gq + qt - 1) / qt;
         std::lock_guard<std::mutex> lock(g_bank_mutex);
@@ -386,14 +395,17 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         SR_CUDA(cudaMemcpyToSymbolAsync(c_qhat, (const float *)e->qhat.p + (size_t)g0 * kF, (size_t)gq * kF * 4, 0,
                                         cudaMemcpyDeviceToDevice, st));
         if (use_bound) {
-            // finer query tiles than the scan's, so that the few sample tiles still occupy every SM
+            // its own (finer) query tiles: the block maxima of a tile live in shared memory
             ScanArgs b = a;
-            b.qt = std::min(qt, 64);
+            b.qt = std::max(1, std::min({qt, 64, (int)(48 * 1024 / (nblk * 4))}));
             const int bnqt = (gq + b.qt - 1) / b.qt;
-            const int bgrid = (int)std::min<int64_t>((int64_t)e->sm_count * v.ctas, (int64_t)bnqt * nb);
-            Scope sc(e, st, kBound);
-            SR_CUDA(v.bound(b, nb, (int)(full_tiles / nb), bgrid, (size_t)b.qt * 4, st));
-            bound_finish_kernel<<<(gq + 127) / 128, 128, 0, st>>>(a.gbound, a.g_best, gq);
+            const int bgrid = (int)std::min<int64_t>((int64_t)e->sm_count * v.ctas, (int64_t)bnqt * n_sample);
+            uint32_t *gmax = (uint32_t *)e->gbound.p + (size_t)g0 * nblk;
+            {
+                Scope sc(e, st, kBound);
+                SR_CUDA(v.bound(b, nblk, n_sample, (int)(full_tiles / n_sample), gmax, bgrid, (size_t)b.qt * nblk * 4, st));
+            }
+            bound_finish_kernel<<<(gq + 127) / 128, 128, 0, st>>>(gmax, nblk, a.g_best, gq);
             SR_CUDA(cudaGetLastError());
             ++e->launches;
         }

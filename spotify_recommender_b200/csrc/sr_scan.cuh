@@ -64,7 +64,6 @@ struct ScanArgs {
     uint32_t *g_best;        // [nq] orderable score: best known lower bound of the final K-th best
     uint64_t *gslot;         // [nq][K] lock-free global feedback: slot (id mod K) holds the best exact
                              // key any CTA has found among the songs with that residue (atomicMax)
-    uint32_t *gbound;        // [nq] bound pass: min over K+1 sample tiles of the tile's best filter score
     unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] inserts
 };
 
@@ -584,26 +583,30 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 }
 
 // ---- bound pass ---------------------------------------------------------------------------
-// Threshold bootstrap at filter speed.  For K+1 evenly spaced FULL song tiles and every query
-// of the group: the best filter score of the tile (12 FFMA per pair, same loop as the scan, a
-// max instead of a sign test).  Each tile's best belongs to a distinct song, at most one of
-// them the query song itself, so the minimum over the K+1 tiles is a lower bound of the K-th
-// best filter score among real candidates -- no selection, no sorting, < 1 % (K = 10) of a
-// full pass, and ~15x more selective than the K-th best of a 1024-song exact sample.
+// Threshold bootstrap at filter speed.  `n_sample` evenly spaced FULL tiles are scored for
+// every query of the group (12 FFMA per pair, same loop as the scan, a max instead of a sign
+// test).  Their songs are split into K+1 disjoint blocks by the residue of the owning layout
+// thread, so every block spans all sample tiles (and with them every cluster of the store that
+// is at least store/n_sample long -- e.g. every genre of a genre-sorted store).  Each block's
+// best filter score belongs to a distinct song, at most one of them the query song itself, so
+// the minimum over the K+1 block maxima is a lower bound of the K-th best filter score among
+// real candidates: no selection, no sorting, ~2.5 % of a full pass.
 // Unit u = (query tile, sample tile); each CTA takes whole units.
 template <int S, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) bound_kernel(const ScanArgs a, int nb, int stride)
+__global__ void __launch_bounds__(THREADS, MINB) bound_kernel(const ScanArgs a, int nblk, int n_sample, int stride,
+                                                              uint32_t *gmax)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *s_max = reinterpret_cast<uint32_t *>(smem_raw);  // [qt] orderable best score of this unit
+    uint32_t *s_max = reinterpret_cast<uint32_t *>(smem_raw);  // [qt][nblk] orderable block maxima of this unit
     const int tid = threadIdx.x;
+    const int blk = (tid % kLT) % nblk;
     const int nqt = (a.nq + a.qt - 1) / a.qt;
-    for (int u = blockIdx.x; u < nqt * nb; u += gridDim.x) {
+    for (int u = blockIdx.x; u < nqt * n_sample; u += gridDim.x) {
         int qtile = 0, j = u;
-        while (j >= nb) { j -= nb; ++qtile; }
+        while (j >= n_sample) { j -= n_sample; ++qtile; }
         const int q0 = qtile * a.qt;
         const int nql = min(a.qt, a.nq - q0);
-        for (int i = tid; i < nql; i += THREADS) s_max[i] = kOrdNegInf;
+        for (int i = tid; i < nql * nblk; i += THREADS) s_max[i] = 0u;
         __syncthreads();
         const int64_t ltile = (int64_t)j * stride * (THREADS / kLT) + tid / kLT;
         float2 fp[S / 2][kF];
@@ -627,25 +630,30 @@ __global__ void __launch_bounds__(THREADS, MINB) bound_kernel(const ScanArgs a, 
 #pragma unroll
             for (int p = 0; p < S / 2; ++p) m = fmaxf(m, fmaxf(acc[p].x, acc[p].y));  // NaN (irregular) rows are ignored
             const uint32_t o = f2ord(m);
-            if (o > s_max[ql]) atomicMax(&s_max[ql], o);
+            if (o > s_max[ql * nblk + blk]) atomicMax(&s_max[ql * nblk + blk], o);
         }
         __syncthreads();
-        for (int i = tid; i < nql; i += THREADS) atomicMin(a.gbound + q0 + i, s_max[i]);
+        for (int i = tid; i < nql * nblk; i += THREADS)
+            if (s_max[i]) atomicMax(gmax + (size_t)q0 * nblk + i, s_max[i]);
         __syncthreads();
     }
 }
 
-// K+1 disjoint tiles each hold a song whose filter score is >= gbound, at most one of them
-// the query song itself: the exact K-th best is >= gbound - kBoundSlack.  Folded into g_best
-// here rather than in the scan's prologue (ptxas drops the scan's uniform-register operands
-// when this arithmetic is inlined there).
-__global__ void bound_finish_kernel(const uint32_t *gbound, uint32_t *g_best, int nq)
+// K+1 disjoint blocks each hold a song whose filter score is >= the block maximum, at most
+// one of them the query song itself: the exact K-th best is >= min(block maxima) - kBoundSlack.
+// Folded into g_best here rather than in the scan's prologue (ptxas drops the scan's
+// uniform-register operands when this arithmetic is inlined there).
+__global__ void bound_finish_kernel(const uint32_t *gmax, int nblk, uint32_t *g_best, int nq)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    const uint32_t gb = gbound[q];
-    if (gb == 0xFFFFFFFFu) return;
-    const uint32_t o = f2ord(ord2f(gb) - kBoundSlack);
+    uint32_t mn = 0xFFFFFFFFu;
+    for (int r = 0; r < nblk; ++r) {
+        const uint32_t v = gmax[(size_t)q * nblk + r];
+        mn = v < mn ? v : mn;
+    }
+    if (mn == 0u || mn == 0xFFFFFFFFu) return;  // an empty block: no bound
+    const uint32_t o = f2ord(ord2f(mn) - kBoundSlack);
     if (o > g_best[q]) g_best[q] = o;
 }
 
