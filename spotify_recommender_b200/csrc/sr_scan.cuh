@@ -377,12 +377,11 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     int *s_flag = reinterpret_cast<int *>(c.hit + (size_t)a.qt * a.cap);
     int *s_redo_cnt = s_flag + 4;                 // [2]
     int *s_redo = s_redo_cnt + 4;                 // [2][qt] queries whose tile must be re-filtered
-    if (threadIdx.x < 3) s_flag[threadIdx.x] = 0;
+    if (threadIdx.x < 4) s_flag[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_redo_cnt[threadIdx.x] = 0;
     int tphase = 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned hits = 0;
     // this CTA's contiguous run of (query tile, song tile) units; kept in uniform
     // arithmetic (no division) so the constant-bank query index stays warp-uniform and
     // the FFMA2 query operand can live in a uniform register
@@ -414,7 +413,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         for (int tile = t0; tile < t1; ++tile) {
             const int64_t stile = (int64_t)tile * a.tile_stride;  // store tile
             const int64_t ltile = stile * SUB + tid / kLT;      // this thread's layout tile
-            const int64_t row0 = ltile * (S * kLT) + tid % kLT;  // its songs: row0 + s * kLT
+            const int row0 = (int)(ltile * (S * kLT)) + tid % kLT;  // its songs: row0 + s * kLT (ids are 32-bit)
 
             // ---- S songs of the normalised store into registers: S/2 interleaved pairs,
             // six 128-bit loads each, every load two ready FFMA2 operands
@@ -435,9 +434,6 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             // a settle phase follows this tile if some hit buffer fills up (flagged by the thread
             // whose append crosses the mark), and always after the last tile of the segment
             const bool forced = (tile == t1 - 1);
-            // thresholds other CTAs published meanwhile: requested now, consumed after the hot loop
-            uint32_t g_pre = 0;
-            if (warp + WARPS * lane < nql) g_pre = __ldcg(a.g_best + c.qid[warp + WARPS * lane]);
 
             auto append = [&](int ql, const float2 (&acc)[S / 2]) {
 #pragma unroll
@@ -446,12 +442,12 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     for (int h = 0; h < 2; ++h) {
                         const float v = h ? acc[p].y : acc[p].x;
                         if ((int)__float_as_uint(v) >= 0) {
-                            const int64_t row = row0 + (int64_t)(2 * p + h) * kLT;
-                            if (row < a.n) {
+                            const int row = row0 + (2 * p + h) * kLT;
+                            if ((int64_t)row < a.n) {
                                 const int slot = atomicAdd(&c.cnt[ql], 1);
-                                if (slot < a.cap) c.hit[(size_t)ql * a.cap + slot] = (uint32_t)(a.id_base + (int32_t)row);
+                                if (slot < a.cap) c.hit[(size_t)ql * a.cap + slot] = (uint32_t)(a.id_base + row);
                                 if (slot + 1 >= a.settle_at) s_flag[tphase] = 1;
-                                ++hits;
+                                atomicAdd(&s_flag[3], 1);  // statistics only
                             }
                         }
                     }
@@ -491,16 +487,18 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 }
             }
             // ---- tile epilogue: warp w looks after queries ql == w (mod WARPS), one lane each:
-            // adopt thresholds published by other CTAs (g_pre was loaded before the hot loop, so
-            // its latency is hidden), and settle hit buffers that filled up -- every non-empty
+            // adopt thresholds published by other CTAs and settle hit buffers that filled up -- every non-empty
             // one after a segment's first and last tile.  One barrier when there is nothing to
             // settle (threshold updates racing with other warps' reads are benign: any published
             // threshold is a valid lower bound), two when there is.
             {
                 const int ql_mine = warp + WARPS * lane;
-                if (ql_mine < nql && g_pre > c.best[ql_mine]) {
-                    c.best[ql_mine] = g_pre;
-                    c.nthr[ql_mine] = neg_threshold(g_pre);
+                if (ql_mine < nql) {
+                    const uint32_t g = __ldcg(a.g_best + c.qid[ql_mine]);
+                    if (g > c.best[ql_mine]) {
+                        c.best[ql_mine] = g;
+                        c.nthr[ql_mine] = neg_threshold(g);
+                    }
                 }
             }
             __syncthreads();  // all hits of this tile are in the buffers
@@ -564,22 +562,32 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         }
         // ---- segment epilogue: hand this CTA's exact survivors to the per-query pool
         // (the last tile's settle phase and its closing barrier have just run)
+        // (only keys that can still make the final top-K: score >= the best known bound)
         for (int ql = warp; ql < nql; ql += WARPS) {
             const int n = c.lcnt[ql];
             if (n == 0) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(a.pool_cnt + q0 + ql, n);
-            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint64_t floor_key = (uint64_t)max(c.best[ql], __ldcg(a.g_best + c.qid[ql])) << 32;
             uint64_t *slab = a.pool + (size_t)(q0 + ql) * a.segs * a.K;
             const uint64_t *list = c.list + (size_t)ql * a.K;
-            for (int i = lane; i < n; i += 32) slab[base + i] = list[i];
+            for (int b0 = 0; b0 < n; b0 += 32) {
+                const int i = b0 + lane;
+                const uint64_t k = (i < n) ? list[i] : 0ull;
+                const bool keep = k != 0ull && k >= floor_key;
+                const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                if (!m) continue;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(a.pool_cnt + q0 + ql, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) slab[base + __popc(m & ((1u << lane) - 1u))] = k;
+            }
         }
         __syncthreads();
         u += (t1 - t0);
         t0 = 0;
         ++qtile;
     }
-    if (a.stats && hits) atomicAdd(a.stats + 0, (unsigned long long)hits);
+    __syncthreads();
+    if (a.stats && tid == 0 && s_flag[3]) atomicAdd(a.stats + 0, (unsigned long long)s_flag[3]);
 }
 
 // ---- bound pass ---------------------------------------------------------------------------

@@ -214,3 +214,42 @@ def test_sharded_host_logic_single_rank_on_torch_stream(eng, oracle):
         want = oracle.query_index(f, qs[b], k, threads=8)
         assert_exact((outs[b][0].cpu().numpy(), outs[b][1].cpu().numpy()), want)
         assert_exact(sh.query_by_index(qs[b], k), want)
+
+
+def test_all_pairs_neighbour_table(eng, oracle):
+    """BASELINE config 5 at test size: every song's top-K neighbours, streamed in batches."""
+    n, k = 20_000, 10
+    f = synth.features(n)
+    eng.load_features(f)
+    try:
+        eng.set_option("batch", 3000)  # ragged last batch
+        gi, gs = eng.all_pairs_topk(0, n, k)
+        part_i, part_s = eng.all_pairs_topk(7000, 9000, k)  # a query shard of the table
+    finally:
+        eng.set_option("batch", 8192)
+    want = oracle.query_index(f, np.arange(n, dtype=np.int32), k, threads=8)
+    assert_exact((gi, gs), want)
+    assert np.array_equal(part_i, want[0][7000:9000])
+    # symmetry of the reference's arithmetic (SURVEY 8e): s(i, j) == s(j, i) bit for bit
+    j = gi[:, 0]
+    back = np.array([oracle.scores(f[jj:jj + 1], f[i])[0] for i, jj in list(enumerate(j))[:200]], np.float32)
+    assert np.array_equal(back.view(np.uint32), gs[:200, 0].view(np.uint32))
+
+
+def test_clustered_store_takes_the_refilter_path(eng, oracle):
+    """A genre-sorted store whose clusters the bound pass cannot see (bound off, tiny sample):
+    tiles overflow their hit buffers and are re-filtered against the raised threshold."""
+    n, k = 300_000, 10
+    rng = np.random.default_rng(9)
+    centers = rng.random((30, 12), dtype=np.float32)
+    f = (centers[np.arange(n) // (n // 30 + 1)] + 0.02 * rng.random((n, 12), dtype=np.float32)).astype(np.float32)
+    eng.load_features(f)
+    q = synth.query_indices(64, n)
+    try:
+        eng.set_option("bound", 0); eng.set_option("sample", 0); eng.set_option("reset", 1)
+        got = eng.query_by_index(q, k)
+        assert eng.stat("refilters") > 0
+    finally:
+        eng.set_option("bound", 1); eng.set_option("sample", -1)
+    assert_exact(got, oracle.query_index(f, q, k, threads=8))
+    assert_exact(eng.query_by_index(q, k), oracle.query_index(f, q, k, threads=8))
