@@ -119,7 +119,8 @@ int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k,
  *   "batch"     max queries per internal pass (workspace is sized for it)
  *   "sample"    threshold-bootstrap sample size per query (0 = off, else power of two <= 4096)
  *   "hit_cap"   hit-buffer entries per query per CTA (multiple of 32; 0 = sized from k)
- *   "settle_at" hits after which a query's buffer is scored and merged (0 = hit_cap / 4)
+ *   "trigger_at" a settle phase starts when some hit buffer holds this many ids (0 = cap / 2)
+ *   "settle_at" ... and scores and merges every buffer holding at least this many (0 = cap / 16)
  *   "bound"     0: skip the bound pass (threshold bootstrap at filter speed)
  *   "profile"   1: bracket every kernel with CUDA events (read with sr_engine_get_timing)
  *   "reset"     any value: zero the counters and timings below               */

@@ -106,7 +106,8 @@ struct sr_engine {
     int batch = 8192;
     int sample = -1;  // -1: automatic
     bool bound = true;  // bound pass (filter-speed threshold bootstrap)
-    int settle_at = 0;  // 0: hit_cap / 4
+    int settle_at = 0;  // 0: cap / 16
+    int trigger_at = 0; // 0: cap / 2
     int hit_cap = 0;   // hit-buffer entries per query in shared memory (0: sized from K)
     bool profile = false;
 
@@ -381,7 +382,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.n_tiles = n_tiles;
         a.qraw = (float *)e->qraw.p + (size_t)g0 * kF; a.qn = (float *)e->qn.p + g0;
         a.exclude = (int32_t *)e->excl.p + g0; a.nq = gq; a.qt = qt;
-        a.K = K; a.cap = cap; a.settle_at = e->settle_at > 0 ? std::min(e->settle_at, cap) : std::max(1, cap / 4);
+        a.K = K; a.cap = cap; a.settle_at = e->settle_at > 0 ? std::min(e->settle_at, cap) : std::max(4, cap / 16);
+        a.trigger_at = e->trigger_at > 0 ? std::min(std::max(e->trigger_at, a.settle_at), cap) : std::max(a.settle_at, cap / 2);
         a.gslot = (uint64_t *)e->gslot.p + (size_t)g0 * K;
         a.pool = (uint64_t *)e->pool.p + (size_t)g0 * segs * K; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
         a.segs = segs;
@@ -719,6 +721,9 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "settle_at")) {
         if (value < 0 || value > 1024) return fail(e, SR_EINVAL, "settle_at must be in [0, 1024]");
         e->settle_at = (int)value;
+    } else if (!strcmp(key, "trigger_at")) {
+        if (value < 0 || value > 1024) return fail(e, SR_EINVAL, "trigger_at must be in [0, 1024]");
+        e->trigger_at = (int)value;
     } else if (!strcmp(key, "bound")) {
         e->bound = value != 0;
     } else if (!strcmp(key, "hit_cap")) {

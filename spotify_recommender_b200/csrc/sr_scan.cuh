@@ -56,7 +56,8 @@ struct ScanArgs {
     int qt;                  // queries per tile (<= kQTMax)
     int K;
     int cap;                 // hit-buffer entries per query (shared memory)
-    int settle_at;           // settle a query's hit buffer once it holds this many
+    int settle_at;           // a settle phase scores every hit buffer holding at least this many ids ...
+    int trigger_at;          // ... and is triggered when some buffer reaches this many (>= settle_at)
     // per-query exact survivors of every CTA segment, merged by finalize_kernel
     uint64_t *pool;          // [nq][segs * K] exact keys
     int32_t *pool_cnt;       // [nq] keys in the pool slab
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                             if ((int64_t)row < a.n) {
                                 const int slot = atomicAdd(&c.cnt[ql], 1);
                                 if (slot < a.cap) c.hit[(size_t)ql * a.cap + slot] = (uint32_t)(a.id_base + row);
-                                if (slot + 1 >= a.settle_at) s_flag[tphase] = 1;
+                                if (slot + 1 >= a.trigger_at) s_flag[tphase] = 1;
                                 atomicAdd(&s_flag[3], 1);  // statistics only
                             }
                         }
