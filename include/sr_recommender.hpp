@@ -65,6 +65,13 @@ public:
     std::vector<std::vector<Recommendation> > recommendBatch(const std::vector<int> &songIndices, int topN);
     /* Dense entry point for embedders that do not hold a vector<Song>. */
     bool initializeDense(const float *features, long long count);
+    /* Load path without the vector<Song> detour: reads a songs_data.bin
+     * written by the reference's DataManager::preprocessData (DataManager.cpp:321-342,
+     * Song.h:35-54 -- native size_t / int / float, no magic) straight into the dense
+     * feature matrix and the lookup indexes.  Unlike DataManager::loadData
+     * (DataManager.cpp:363-409) every length is bounds-checked; a truncated or
+     * implausible file fails with a message instead of reading garbage. */
+    bool initializeFromFile(const std::string &binaryPath);
     /* Lookups as the reference resolves them; -1 when absent. */
     int findSongByTrackId(const std::string &trackId) const;
     int findSongByName(const std::string &trackName) const;

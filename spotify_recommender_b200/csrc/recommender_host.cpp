@@ -9,6 +9,7 @@
 #include <cctype>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <unordered_map>
 
@@ -68,6 +69,93 @@ bool Recommender::initializeDense(const float *features, long long count)
     numSongs = (int)count;
     initialized = true;
     gpuEnabled = true;
+    return true;
+}
+
+namespace {
+// bounds-checked cursor over the file image
+struct Cursor {
+    const unsigned char *p, *end;
+    bool ok = true;
+    bool take(void *dst, size_t n)
+    {
+        if (!ok || (size_t)(end - p) < n) { ok = false; return false; }
+        std::memcpy(dst, p, n);
+        p += n;
+        return true;
+    }
+    bool take_string(std::string *s, size_t limit)
+    {
+        uint64_t len = 0;
+        if (!take(&len, sizeof len) || len > limit || (uint64_t)(end - p) < len) { ok = false; return false; }
+        if (s) s->assign(reinterpret_cast<const char *>(p), (size_t)len);
+        p += len;
+        return true;
+    }
+};
+}  // namespace
+
+bool Recommender::initializeFromFile(const std::string &binaryPath)
+{
+    std::cout << "Initializing recommender (B200 engine) from " << binaryPath << "..." << std::endl;
+    initialized = false;
+    gpuEnabled = false;
+    std::ifstream in(binaryPath, std::ios::binary | std::ios::ate);
+    if (!in.is_open()) {
+        std::cerr << "Error: Could not open binary file: " << binaryPath << std::endl;
+        return false;
+    }
+    const std::streamoff size = in.tellg();
+    std::vector<unsigned char> image((size_t)std::max<std::streamoff>(size, 0));
+    in.seekg(0);
+    if (size <= 0 || !in.read(reinterpret_cast<char *>(image.data()), size)) {
+        std::cerr << "Error: Could not read binary file: " << binaryPath << std::endl;
+        return false;
+    }
+    Cursor cur{image.data(), image.data() + image.size()};
+    uint64_t numSongs = 0, numGenres = 0;
+    cur.take(&numSongs, sizeof numSongs);   // DataManager.cpp:321-323
+    cur.take(&numGenres, sizeof numGenres); // DataManager.cpp:325-327
+    // every song takes at least 3 lengths + genre id + 12 floats = 76 bytes
+    if (!cur.ok || numSongs == 0 || numSongs > 0x7fffffffULL || numSongs > image.size() / 76 || numGenres > image.size() / 12) {
+        std::cerr << "Error: " << binaryPath << " is not a songs_data.bin (implausible header)" << std::endl;
+        return false;
+    }
+    for (uint64_t g = 0; g < numGenres && cur.ok; ++g) {  // genre table (DataManager.cpp:329-337): skipped
+        int32_t id;
+        cur.take(&id, sizeof id);
+        cur.take_string(nullptr, 1 << 20);
+    }
+    const size_t n = (size_t)numSongs;
+    std::vector<float> dense(n * FEATURE_COUNT);
+    impl->by_id.clear();
+    impl->by_lower_name.clear();
+    impl->lower_blob.clear();
+    impl->lower_off.assign(1, 0u);
+    impl->by_id.reserve(n * 2);
+    impl->by_lower_name.reserve(n * 2);
+    std::string id, name;
+    for (size_t i = 0; i < n && cur.ok; ++i) {  // Song::serialize order (Song.h:35-54)
+        int32_t genre;
+        cur.take_string(&id, 1 << 20);
+        cur.take_string(&name, 1 << 20);
+        cur.take_string(nullptr, 1 << 20);  // artists: not needed by the scoring engine
+        cur.take(&genre, sizeof genre);
+        cur.take(&dense[i * FEATURE_COUNT], sizeof(float) * FEATURE_COUNT);
+        if (!cur.ok) break;
+        impl->by_id.emplace(id, (int)i);
+        std::string l = lower(name);
+        impl->by_lower_name.emplace(l, (int)i);
+        impl->lower_blob.append(l);
+        impl->lower_blob.push_back('\0');
+        impl->lower_off.push_back((uint32_t)impl->lower_blob.size());
+    }
+    if (!cur.ok) {
+        std::cerr << "Error: " << binaryPath << " is truncated or corrupt" << std::endl;
+        return false;
+    }
+    if (!initializeDense(dense.data(), (long long)n)) return false;
+    std::cout << "Recommender initialized on GPU: " << numSongs << " songs resident" << std::endl;
     return true;
 }
 
@@ -211,6 +299,21 @@ void *sr_recommender_create(const float *features, int64_t n, const char *const 
     Recommender *r = new Recommender();
     std::streambuf *old = std::cout.rdbuf(nullptr);
     const bool ok = r->initialize(songs);
+    std::cout.rdbuf(old);
+    if (!ok) {
+        delete r;
+        return nullptr;
+    }
+    return r;
+}
+
+// Straight from a songs_data.bin written by the reference's --preprocess.
+void *sr_recommender_create_from_file(const char *path)
+{
+    if (!path) return nullptr;
+    Recommender *r = new Recommender();
+    std::streambuf *old = std::cout.rdbuf(nullptr);
+    const bool ok = r->initializeFromFile(path);
     std::cout.rdbuf(old);
     if (!ok) {
         delete r;

@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "spotify_recommender_b200", "libsr_recommender.so")
-EXPORTS = ["sr_recommender_create", "sr_recommender_destroy", "sr_recommender_song_count", "sr_recommender_gpu_enabled",
+EXPORTS = ["sr_recommender_create", "sr_recommender_create_from_file", "sr_recommender_destroy", "sr_recommender_song_count", "sr_recommender_gpu_enabled",
            "sr_recommender_by_index", "sr_recommender_by_name", "sr_recommender_by_id", "sr_recommender_find_name",
            "sr_recommender_find_id"]
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
@@ -20,6 +20,8 @@ def load():
     L = C.CDLL(SO)
     L.sr_recommender_create.restype = C.c_void_p
     L.sr_recommender_create.argtypes = [_f32p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.sr_recommender_create_from_file.restype = C.c_void_p
+    L.sr_recommender_create_from_file.argtypes = [C.c_char_p]
     L.sr_recommender_destroy.argtypes = [C.c_void_p]
     L.sr_recommender_song_count.argtypes = [C.c_void_p]
     L.sr_recommender_gpu_enabled.argtypes = [C.c_void_p]
@@ -32,6 +34,16 @@ def load():
 
 
 class HostRecommender:
+    @classmethod
+    def from_file(cls, path: str):
+        self = cls.__new__(cls)
+        self.L = load()
+        self.h = self.L.sr_recommender_create_from_file(path.encode())
+        if not self.h:
+            raise RuntimeError(f"initializeFromFile({path}) failed")
+        self.n = int(self.L.sr_recommender_song_count(self.h))
+        return self
+
     def __init__(self, feats, ids=None, names=None):
         self.L = load()
         feats = np.ascontiguousarray(feats, np.float32)

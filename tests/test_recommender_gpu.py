@@ -128,3 +128,20 @@ def test_reference_cli_end_to_end(tmp_path):
         assert len(ids_b) > 1 and ids_a == ids_b, (ids_a, ids_b)
     rc, _, _ = ids(b200, "--song", "definitely not a track name")
     assert rc == 1
+
+    # the same songs_data.bin straight into the engine, no vector<Song>
+    from recommender_lib import HostRecommender
+    rec = HostRecommender.from_file(str(tmp_path / "songs_data.bin"))
+    assert rec.n == 4999
+    _, want, _ = ids(cpu, "--song", "Track 500", "-n", "10")
+    got = rec.by_name("Track 500", 10)
+    # the CLI prints the query song's id first, then the recommendations; map the engine's
+    # indices back to track ids through the id lookup of the class itself
+    assert len(want) == 11 and got.size == 10
+    assert rec.find_id(want[0]) == rec.find_name("Track 500")
+    assert all(rec.find_id(w) == int(g) for w, g in zip(want[1:], got))
+    rec.close()
+    bad = tmp_path / "truncated.bin"
+    bad.write_bytes((tmp_path / "songs_data.bin").read_bytes()[:100_000])
+    with pytest.raises(RuntimeError):
+        HostRecommender.from_file(str(bad))
