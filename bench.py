@@ -282,28 +282,36 @@ def run_ours(args) -> None:
         "algorithmic": f"{FLOP_PER_PAIR} flop/pair x {pairs_per_launch:.3e} pairs per launch",
         "other_kernels_ms_per_step": other,
     }
-    # the HBM-bound regime of the same kernel (Q <= 16: one pass over the store per batch)
+    # the HBM-bound regime of the same kernels (Q < Q* = 23 queries: one pass over the store per call)
     hbm = None
     if rank == 0 and world == 1:
         try:
-            q16 = q_dev[0][:16].contiguous()
-            o16 = torch.empty((16, TOPK), dtype=torch.int32, device=dev)
-            for _ in range(3):
-                eng.query_by_index_dev(q16, 16, TOPK, o16, None, stream.cuda_stream)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(10):
-                eng.query_by_index_dev(q16, 16, TOPK, o16, None, stream.cuda_stream)
-            b.record(stream)
-            torch.cuda.synchronize()
-            t16 = a.elapsed_time(b) / 10 * 1e-3
-            gbs = BYTES_PER_SONG * float(hi - lo) / t16 / 1e9
             hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
-            hbm = {"workload": f"16 queries x {hi - lo} songs, top-{TOPK}, whole call (4 kernels)", "bound": "hbm",
-                   "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+            hbm = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
                    "peak_is": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6650 GB/s",
-                   "ms_per_call": t16 * 1e3}
+                   "algorithmic": f"{BYTES_PER_SONG} B/song x {hi - lo} songs per call", "cases": []}
+            for nq_small in (1, 4, 16):
+                qs = q_dev[0][:nq_small].contiguous()
+                os_ = torch.empty((nq_small, TOPK), dtype=torch.int32, device=dev)
+                for _ in range(3):
+                    eng.query_by_index_dev(qs, nq_small, TOPK, os_, None, stream.cuda_stream)
+                torch.cuda.synchronize()
+                eng.set_option("profile", 1)
+                eng.set_option("reset", 1)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(20):
+                    eng.query_by_index_dev(qs, nq_small, TOPK, os_, None, stream.cuda_stream)
+                b_.record(stream)
+                torch.cuda.synchronize()
+                t_call = a.elapsed_time(b_) / 20 * 1e-3
+                t_scan = eng.timing("scan")[0] / 20 * 1e-3
+                eng.set_option("profile", 0)
+                nbytes = BYTES_PER_SONG * float(hi - lo)
+                hbm["cases"].append({"queries": nq_small, "ms_per_call": t_call * 1e3, "scan_kernel_ms": t_scan * 1e3,
+                                     "achieved_call": nbytes / t_call / 1e9, "frac_call": nbytes / t_call / 1e9 / hbm_peak,
+                                     "achieved_scan_kernel": nbytes / t_scan / 1e9,
+                                     "frac_scan_kernel": nbytes / t_scan / 1e9 / hbm_peak})
         except Exception as exc:  # never lose the headline over the side measurement
             hbm = {"error": str(exc)}
 

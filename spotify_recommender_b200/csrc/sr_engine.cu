@@ -383,6 +383,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.qraw = (float *)e->qraw.p + (size_t)g0 * kF; a.qn = (float *)e->qn.p + g0;
         a.exclude = (int32_t *)e->excl.p + g0; a.nq = gq; a.qt = qt;
         a.K = K; a.cap = cap; a.settle_at = e->settle_at > 0 ? std::min(e->settle_at, cap) : std::max(4, cap / 16);
+        a.refresh_every = std::max(1, std::min(8, 64 / qt));
         a.trigger_at = e->trigger_at > 0 ? std::min(std::max(e->trigger_at, a.settle_at), cap) : std::max(a.settle_at, cap / 2);
         a.gslot = (uint64_t *)e->gslot.p + (size_t)g0 * K;
         a.pool = (uint64_t *)e->pool.p + (size_t)g0 * segs * K; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;

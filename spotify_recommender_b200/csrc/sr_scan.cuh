@@ -58,6 +58,8 @@ struct ScanArgs {
     int cap;                 // hit-buffer entries per query (shared memory)
     int settle_at;           // a settle phase scores every hit buffer holding at least this many ids ...
     int trigger_at;          // ... and is triggered when some buffer reaches this many (>= settle_at)
+    int refresh_every;       // tiles between two looks at the thresholds other CTAs published (an L2 round
+                             // trip: every tile for large query tiles, rarer when a tile is only a few queries)
     // per-query exact survivors of every CTA segment, merged by finalize_kernel
     uint64_t *pool;          // [nq][segs * K] exact keys
     int32_t *pool_cnt;       // [nq] keys in the pool slab
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             // threshold is a valid lower bound), two when there is.
             {
                 const int ql_mine = warp + WARPS * lane;
-                if (ql_mine < nql) {
+                if (ql_mine < nql && (tile - t0) % a.refresh_every == 0) {
                     const uint32_t g = __ldcg(a.g_best + c.qid[ql_mine]);
                     if (g > c.best[ql_mine]) {
                         c.best[ql_mine] = g;
