@@ -28,19 +28,19 @@ typedef cudaError_t (*ScanOcc)(int *ctas_per_sm, size_t smem);
 typedef cudaError_t (*BoundLaunch)(const ScanArgs &, int nblk, int n_sample, int stride, uint32_t *gmax, int grid, size_t smem,
                                    cudaStream_t st);
 
-template <int S, int T, int M, bool D>
+template <int S, int T, int M, bool D, bool G>
 cudaError_t launch_scan(const ScanArgs &a, int grid, size_t smem, cudaStream_t st)
 {
-    auto k = scan_kernel<S, T, M, D>;
+    auto k = scan_kernel<S, T, M, D, G>;
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     k<<<grid, T, smem, st>>>(a);
     return cudaGetLastError();
 }
-template <int S, int T, int M, bool D>
+template <int S, int T, int M, bool D, bool G>
 cudaError_t occ_scan(int *ctas, size_t smem)
 {
-    auto k = scan_kernel<S, T, M, D>;
+    auto k = scan_kernel<S, T, M, D, G>;
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k, T, smem);
@@ -60,21 +60,26 @@ cudaError_t launch_bound(const ScanArgs &a, int nblk, int n_sample, int stride, 
 struct Variant {
     const char *name;
     int S, threads, ctas;
+    bool staged;
     ScanLaunch launch;
     ScanOcc occ;
     BoundLaunch bound;
 };
 #define SR_VARIANT(S, T, M, D) \
-    {"S" #S "xT" #T "x" #M "-" #D, S, T, M, launch_scan<S, T, M, D>, occ_scan<S, T, M, D>, launch_bound<S, T, M>}
+    {"S" #S "xT" #T "x" #M "-" #D, S, T, M, false, launch_scan<S, T, M, D, false>, occ_scan<S, T, M, D, false>, launch_bound<S, T, M>}
+#define SR_VARIANT_TMA(S, T, M) \
+    {"S" #S "xT" #T "x" #M "-tma", S, T, M, true, launch_scan<S, T, M, true, true>, occ_scan<S, T, M, true, true>, launch_bound<S, T, M>}
 const Variant kVariants[] = {
     SR_VARIANT(8, 256, 2, false),
     SR_VARIANT(8, 256, 2, true),
     SR_VARIANT(8, 512, 1, false),
     SR_VARIANT(8, 512, 1, true),
     SR_VARIANT(4, 256, 4, true),
+    SR_VARIANT_TMA(8, 256, 1),
+    SR_VARIANT_TMA(8, 256, 2),
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-constexpr int kAutoSmall = 1, kAutoLarge = 3, kAutoS = 8;
+constexpr int kAutoSmall = 6, kAutoLarge = 3, kAutoS = 8;
 
 enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kBound, kNumKernels };
 const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge", "bound"};
@@ -281,9 +286,10 @@ cudaEvent_t g_bank_event[64] = {nullptr};
 int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const int32_t *d_excl, int nq, int K,
              int32_t *d_out_idx, float *d_out_score, cudaStream_t st)
 {
-    // small batches are HBM-bound: two 256-thread CTAs per SM overlap one CTA's tile load with
-    // the other's arithmetic; large batches are FP32-bound: one 512-thread CTA, bigger tiles
-    const int vi = e->variant >= 0 ? e->variant : (nq <= 48 ? kAutoSmall : kAutoLarge);
+    // small batches are HBM-bound: two 256-thread CTAs per SM, song tiles staged through shared
+    // memory by TMA one tile ahead; large batches are FP32-bound: one 512-thread CTA, bigger
+    // tiles, shared memory spent on 256 queries' lists and hit buffers
+    const int vi = e->variant >= 0 ? e->variant : (nq <= 40 ? kAutoSmall : kAutoLarge);
     e->last_variant = vi;
     const Variant &v = kVariants[vi];
     const int TS = v.S * v.threads;
@@ -295,6 +301,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     // the CTA's exact top-K lists (qt x K keys).  Large qt amortises the per-tile costs; cap of a
     // few K lets an overflowing buffer alone lift the threshold far enough for the re-filter
     // round to converge.  First combination that fits wins.
+    const size_t stage_bytes = v.staged ? (size_t)TS * kF * 4 : 0;
     const size_t smem_budget = (size_t)216 * 1024 / v.ctas;
     const int qt_max = std::max(1, std::min(e->qt_opt, kQTMax));
     const int kk = std::max(K, 32);
@@ -304,14 +311,14 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
                              std::max(128, 3 * kk / 2), qtry <= 64 ? std::max(32, kk) : 0};
         for (int ci = 0; ci < 4 && !qt_cap; ++ci) {
             const int ctry = std::min(1024, (caps[ci] + 31) / 32 * 32);
-            if (ctry > 0 && scan_smem_bytes(qtry, ctry, K) <= smem_budget) { qt_cap = qtry; cap = ctry; }
+            if (ctry > 0 && scan_smem_bytes(qtry, ctry, K, stage_bytes) <= smem_budget) { qt_cap = qtry; cap = ctry; }
         }
     }
     if (!qt_cap) return fail(e, SR_EINVAL, "k = %d does not fit the scan kernel's shared memory", K);
     const int nqt0 = (gsize + qt_cap - 1) / qt_cap;
     const int qt = (gsize + nqt0 - 1) / nqt0;
     const int nqt = (gsize + qt - 1) / qt;
-    const size_t smem = scan_smem_bytes(qt, cap, K);
+    const size_t smem = scan_smem_bytes(qt, cap, K, stage_bytes);
     int ctas = 0;
     SR_CUDA(v.occ(&ctas, smem));
     if (ctas < 1) return fail(e, SR_ECUDA, "scan kernel %s does not fit one SM (smem %zu)", v.name, smem);

@@ -70,9 +70,41 @@ struct ScanArgs {
     unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] inserts
 };
 
-__host__ __device__ inline size_t scan_smem_bytes(int qt, int cap, int K)
+// `stage_bytes`: size of the TMA staging buffer for one song tile (0 for unstaged shapes)
+__host__ __device__ inline size_t scan_smem_bytes(int qt, int cap, int K, size_t stage_bytes = 0)
 {
-    return (size_t)qt * K * 8 + (size_t)qt * (kF + 9 + cap) * 4 + 32;
+    return (stage_bytes ? stage_bytes + 16 : 0) + (size_t)qt * K * 8 + (size_t)qt * (kF + 9 + cap) * 4 + 32;
+}
+
+// ---- TMA (bulk async copy) staging of song tiles: global -> shared, completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_tile(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    // the buffer was last read through the generic proxy (LDS): order those reads before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // CTA runs (segments) that can touch one query tile = slab capacity of the pool, in lists:
@@ -350,7 +382,12 @@ __device__ __forceinline__ uint32_t filter_query(const float2 (&fp)[S / 2][kF], 
     return m;  // sign bit clear <=> at least one song passes the filter
 }
 
-template <int S, int THREADS, int MINB, bool DEFER>
+// STAGE: song tiles are brought into shared memory by the bulk-copy (TMA) engine one tile
+// ahead -- issued as soon as the previous tile has been copied into registers -- so the HBM
+// stream never waits for the arithmetic (the shape for small, HBM-bound batches; the large-batch
+// shape spends its shared memory on 256 queries' lists and hit buffers instead and hides the
+// 3 % its tile loads cost behind nothing).
+template <int S, int THREADS, int MINB, bool DEFER, bool STAGE>
 __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 {
     constexpr int TS = S * THREADS;
@@ -361,9 +398,12 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     static_assert(kQTMax <= 32 * WARPS, "one lane per owned query in the tile epilogue");
     static_assert(kRowPad % TS == 0, "store padding must cover whole tiles");
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr uint32_t kTileBytes = (uint32_t)TS * kF * 4;
+    float4 *s_tile = reinterpret_cast<float4 *>(smem_raw);                         // STAGE only
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + kTileBytes);          // STAGE only
     QueryCtx c;
-    c.list = reinterpret_cast<uint64_t *>(smem_raw);
+    c.list = reinterpret_cast<uint64_t *>(smem_raw + (STAGE ? kTileBytes + 16 : 0));
     c.qraw = reinterpret_cast<float *>(c.list + (size_t)a.qt * a.K);
     c.nthr = c.qraw + a.qt * kF;
     c.qn = c.nthr + a.qt;
@@ -392,6 +432,14 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     const int u_end = u + a.upc + ((int)blockIdx.x < a.extra ? 1 : 0);
     int qtile = 0, t0 = u;
     while (t0 >= a.n_tiles) { t0 -= a.n_tiles; ++qtile; }
+    uint32_t sphase = 0;
+    if (STAGE) {
+        if (tid == 0) {
+            mbar_init(s_bar, 1);
+            if (u < u_end) tma_load_tile(s_tile, a.hat + (int64_t)t0 * a.tile_stride * (TS * kF), kTileBytes, s_bar);
+        }
+        __syncthreads();
+    }
 
     while (u < u_end) {
         const int t1 = min(a.n_tiles, t0 + (u_end - u));
@@ -421,7 +469,27 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             // ---- S songs of the normalised store into registers: S/2 interleaved pairs,
             // six 128-bit loads each, every load two ready FFMA2 operands
             float2 fp[S / 2][kF];
-            {
+            if (STAGE) {
+                mbar_wait(s_bar, sphase);  // this tile has landed in shared memory
+                sphase ^= 1u;
+                const float4 *src = s_tile + ((tid / kLT) * (S / 2) * kLT + tid % kLT) * 6;
+#pragma unroll
+                for (int p = 0; p < S / 2; ++p) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 6; ++c4) {
+                        const float4 v = src[p * kLT * 6 + c4];
+                        fp[p][2 * c4] = make_float2(v.x, v.y);
+                        fp[p][2 * c4 + 1] = make_float2(v.z, v.w);
+                    }
+                }
+                __syncthreads();  // every thread has copied its songs out: the buffer is free
+                if (tid == 0) {   // next tile of this run: same query tile, or tile 0 of the next one
+                    int64_t nxt = -1;
+                    if (tile + 1 < t1) nxt = stile + a.tile_stride;
+                    else if (u + (t1 - t0) < u_end) nxt = 0;
+                    if (nxt >= 0) tma_load_tile(s_tile, a.hat + nxt * (TS * kF), kTileBytes, s_bar);
+                }
+            } else {
                 const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (ltile * (S / 2) * kLT + tid % kLT) * 6;
 #pragma unroll
                 for (int p = 0; p < S / 2; ++p) {
