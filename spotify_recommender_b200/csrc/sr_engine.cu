@@ -28,19 +28,19 @@ typedef cudaError_t (*ScanOcc)(int *ctas_per_sm, size_t smem);
 typedef cudaError_t (*BoundLaunch)(const ScanArgs &, int nblk, int n_sample, int stride, uint32_t *gmax, int grid, size_t smem,
                                    cudaStream_t st);
 
-template <int S, int T, int M, bool D, bool G>
+template <int S, int T, int M, bool D, bool G, bool Y>
 cudaError_t launch_scan(const ScanArgs &a, int grid, size_t smem, cudaStream_t st)
 {
-    auto k = scan_kernel<S, T, M, D, G>;
+    auto k = scan_kernel<S, T, M, D, G, Y>;
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     k<<<grid, T, smem, st>>>(a);
     return cudaGetLastError();
 }
-template <int S, int T, int M, bool D, bool G>
+template <int S, int T, int M, bool D, bool G, bool Y>
 cudaError_t occ_scan(int *ctas, size_t smem)
 {
-    auto k = scan_kernel<S, T, M, D, G>;
+    auto k = scan_kernel<S, T, M, D, G, Y>;
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k, T, smem);
@@ -60,15 +60,17 @@ cudaError_t launch_bound(const ScanArgs &a, int nblk, int n_sample, int stride, 
 struct Variant {
     const char *name;
     int S, threads, ctas;
-    bool staged;
+    bool staged, dynamic;
     ScanLaunch launch;
     ScanOcc occ;
     BoundLaunch bound;
 };
 #define SR_VARIANT(S, T, M, D) \
-    {"S" #S "xT" #T "x" #M "-" #D, S, T, M, false, launch_scan<S, T, M, D, false>, occ_scan<S, T, M, D, false>, launch_bound<S, T, M>}
+    {"S" #S "xT" #T "x" #M "-" #D, S, T, M, false, false, launch_scan<S, T, M, D, false, false>, occ_scan<S, T, M, D, false, false>, launch_bound<S, T, M>}
 #define SR_VARIANT_TMA(S, T, M) \
-    {"S" #S "xT" #T "x" #M "-tma", S, T, M, true, launch_scan<S, T, M, true, true>, occ_scan<S, T, M, true, true>, launch_bound<S, T, M>}
+    {"S" #S "xT" #T "x" #M "-tma", S, T, M, true, false, launch_scan<S, T, M, true, true, false>, occ_scan<S, T, M, true, true, false>, launch_bound<S, T, M>}
+#define SR_VARIANT_DYN(S, T, M) \
+    {"S" #S "xT" #T "x" #M "-dyn", S, T, M, false, true, launch_scan<S, T, M, true, false, true>, occ_scan<S, T, M, true, false, true>, launch_bound<S, T, M>}
 const Variant kVariants[] = {
     SR_VARIANT(8, 256, 2, false),
     SR_VARIANT(8, 256, 2, true),
@@ -77,9 +79,11 @@ const Variant kVariants[] = {
     SR_VARIANT(4, 256, 4, true),
     SR_VARIANT_TMA(8, 256, 1),
     SR_VARIANT_TMA(8, 256, 2),
+    SR_VARIANT_DYN(8, 512, 1),
+    SR_VARIANT_DYN(8, 256, 2),
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-constexpr int kAutoSmall = 6, kAutoLarge = 3, kAutoS = 8;
+constexpr int kAutoSmall = 6, kAutoLarge = 7, kStaticLarge = 3, kAutoS = 8;
 
 enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kBound, kNumKernels };
 const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge", "bound"};
@@ -117,7 +121,7 @@ struct sr_engine {
     bool profile = false;
 
     // batch workspace (grow-only)
-    DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, pool_cnt, pool, out_idx, out_score, qin, exin;
+    DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, tile_ctr, pool_cnt, pool, out_idx, out_score, qin, exin;
     unsigned long long *d_stats = nullptr;  // [8]
     unsigned long long *d_irregular = nullptr;
     int32_t *d_flag = nullptr;
@@ -289,31 +293,40 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     // small batches are HBM-bound: two 256-thread CTAs per SM, song tiles staged through shared
     // memory by TMA one tile ahead; large batches are FP32-bound: one 512-thread CTA, bigger
     // tiles, shared memory spent on 256 queries' lists and hit buffers
-    const int vi = e->variant >= 0 ? e->variant : (nq <= 40 ? kAutoSmall : kAutoLarge);
-    e->last_variant = vi;
-    const Variant &v = kVariants[vi];
-    const int TS = v.S * v.threads;
-    const int n_tiles = (int)((e->n + TS - 1) / TS);
-    // query groups (what fits the constant bank), evenly filled; then query tiles inside a group
-    const int groups = (nq + kConstQueries - 1) / kConstQueries;
-    const int gsize = (nq + groups - 1) / groups;
-    // Queries per tile (qt) and hit-buffer entries per query (cap), both in shared memory next to
-    // the CTA's exact top-K lists (qt x K keys).  Large qt amortises the per-tile costs; cap of a
-    // few K lets an overflowing buffer alone lift the threshold far enough for the re-filter
-    // round to converge.  First combination that fits wins.
-    const size_t stage_bytes = v.staged ? (size_t)TS * kF * 4 : 0;
-    const size_t smem_budget = (size_t)216 * 1024 / v.ctas;
-    const int qt_max = std::max(1, std::min(e->qt_opt, kQTMax));
-    const int kk = std::max(K, 32);
-    int qt_cap = 0, cap = 0;
-    for (int qtry = qt_max; qtry >= 1 && !qt_cap; qtry = (qtry > 8 ? qtry / 2 : qtry - 1)) {
-        const int caps[4] = {e->hit_cap > 0 ? e->hit_cap : std::max(128, 4 * kk), std::max(128, 2 * kk),
-                             std::max(128, 3 * kk / 2), qtry <= 64 ? std::max(32, kk) : 0};
-        for (int ci = 0; ci < 4 && !qt_cap; ++ci) {
-            const int ctry = std::min(1024, (caps[ci] + 31) / 32 * 32);
-            if (ctry > 0 && scan_smem_bytes(qtry, ctry, K, stage_bytes) <= smem_budget) { qt_cap = qtry; cap = ctry; }
+    int vi = e->variant >= 0 ? e->variant : (nq <= 40 ? kAutoSmall : kAutoLarge);
+    const Variant *vp = nullptr;
+    int TS = 0, n_tiles = 0, groups = 0, gsize = 0, qt_cap = 0, cap = 0;
+    size_t stage_bytes = 0;
+    for (int attempt = 0; attempt < 2 && !qt_cap; ++attempt) {
+        if (attempt == 1) {  // the staged small-batch shape has little shared memory left for long lists
+            if (e->variant >= 0 || vi == kAutoLarge) break;
+            vi = kAutoLarge;
+        }
+        vp = &kVariants[vi];
+        TS = vp->S * vp->threads;
+        n_tiles = (int)((e->n + TS - 1) / TS);
+        // query groups (what fits the constant bank), evenly filled; then query tiles inside a group
+        groups = (nq + kConstQueries - 1) / kConstQueries;
+        gsize = (nq + groups - 1) / groups;
+        // Queries per tile (qt) and hit-buffer entries per query (cap), both in shared memory next to
+        // the CTA's exact top-K lists (qt x K keys).  Large qt amortises the per-tile costs; cap of a
+        // few K lets an overflowing buffer alone lift the threshold far enough for the re-filter
+        // round to converge.  First combination that fits wins.
+        stage_bytes = vp->staged ? (size_t)TS * kF * 4 : 0;
+        const size_t smem_budget = (size_t)216 * 1024 / vp->ctas;
+        const int qt_max = std::max(1, std::min(e->qt_opt, kQTMax));
+        const int kk = std::max(K, 32);
+        for (int qtry = qt_max; qtry >= 1 && !qt_cap; qtry = (qtry > 8 ? qtry / 2 : qtry - 1)) {
+            const int caps[4] = {e->hit_cap > 0 ? e->hit_cap : std::max(128, 4 * kk), std::max(128, 2 * kk),
+                                 std::max(128, 3 * kk / 2), qtry <= 64 ? std::max(32, kk) : 0};
+            for (int ci = 0; ci < 4 && !qt_cap; ++ci) {
+                const int ctry = std::min(1024, (caps[ci] + 31) / 32 * 32);
+                if (ctry > 0 && scan_smem_bytes(qtry, ctry, K, stage_bytes) <= smem_budget) { qt_cap = qtry; cap = ctry; }
+            }
         }
     }
+    e->last_variant = vi;
+    const Variant &v = *vp;
     if (!qt_cap) return fail(e, SR_EINVAL, "k = %d does not fit the scan kernel's shared memory", K);
     const int nqt0 = (gsize + qt_cap - 1) / qt_cap;
     const int qt = (gsize + nqt0 - 1) / nqt0;
@@ -331,13 +344,14 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         const int64_t gunits = (int64_t)((std::min(gsize, nq - g0) + qt - 1) / qt) * n_tiles;
         upc_min = (int)std::min<int64_t>(upc_min, std::max<int64_t>(1, gunits / std::min<int64_t>(grid, gunits)));
     }
-    const int segs = scan_segs(n_tiles, upc_min);
+    const int segs = std::max(scan_segs(n_tiles, upc_min), grid / std::max(1, nqt) + 3);
 
     // threshold bootstrap: the bound pass (filter speed, per query group) when the store has
     // enough full tiles, else the exact sample
     const int64_t full_tiles = e->n / TS;
     const int nblk = K + 1;                                  // disjoint blocks of sample songs
-    const int n_sample = (int)std::min<int64_t>(128 / (v.threads / kLT), full_tiles / 4);  // sample tiles (128 layout tiles)
+    // sample tiles: 128 layout tiles on large stores, never more than ~6 % of the store
+    const int n_sample = (int)std::min<int64_t>({(int64_t)128 / (v.threads / kLT), std::max<int64_t>(4, full_tiles / 16), full_tiles / 4});
     const bool use_bound = e->bound && nblk <= kLT / 2 && n_sample >= 4 && (int64_t)n_sample * TS >= 64 * (int64_t)nblk;
 
     int rc;
@@ -348,6 +362,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->gbest, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gbound, (size_t)nq * nblk * 4))) return rc;
     if ((rc = ensure(e, e->gslot, (size_t)nq * K * 8))) return rc;
+    if ((rc = ensure(e, e->tile_ctr, (size_t)(nqt + 1) * 4))) return rc;
     if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->pool, (size_t)nq * segs * K * 8))) return rc;
 
@@ -426,8 +441,16 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             const int ggrid = (int)std::min<int64_t>(grid, gunits);
             a.upc = (int)(gunits / ggrid);
             a.extra = (int)(gunits % ggrid);
+            a.cpq = 0;
+            a.tile_ctr = (int *)e->tile_ctr.p;
+            const Variant *vl = &v;
+            if (v.dynamic && gnqt > ggrid) vl = &kVariants[kStaticLarge];  // more query tiles than CTAs: static runs (same S, threads, smem)
+            if (vl->dynamic) {
+                a.cpq = ggrid / gnqt;
+                SR_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, (size_t)gnqt * 4, st));
+            }
             Scope sc(e, st, kScan);
-            SR_CUDA(v.launch(a, ggrid, smem, st));
+            SR_CUDA(vl->launch(a, ggrid, smem, st));
         }
         SR_CUDA(cudaEventRecord(ev, st));
     }
@@ -559,7 +582,7 @@ void sr_engine_destroy(sr_engine *e)
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto &t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->pool_cnt, &e->pool,
+    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->tile_ctr, &e->pool_cnt, &e->pool,
                       &e->out_idx, &e->out_score, &e->qin, &e->exin};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
