@@ -26,8 +26,6 @@ constexpr float kBoundSlack = 4.0e-6f;
 constexpr float kNormLo = 1.0e-3f;
 constexpr float kNormHi = 1.0e15f;
 
-// candidate not yet scored in the oracle's arithmetic: hi word of the key
-constexpr uint32_t kUnscored = 0xFFFFFFFFu;
 
 // ---- order-preserving key encoding ----------------------------------------
 // key = orderable(score) << 32 | (0xFFFFFFFF - id): larger key == better under
@@ -172,59 +170,6 @@ __device__ __forceinline__ int next_pow2(int v)
     int p = 1;
     while (p < v) p <<= 1;
     return p;
-}
-
-// ---- warp-cooperative radix select -------------------------------------------
-// Finds the want-th largest 32-bit value among w(i) for i in [0,cnt) that pass
-// `match(i)`; returns it and the rank still wanted inside its tie group through
-// *rank_in_ties.  hist: 256 counters of shared memory owned by this warp.
-template <typename WordFn>
-__device__ __forceinline__ uint32_t warp_radix_select(int cnt, int want, uint32_t *hist, WordFn word,
-                                                      int *rank_in_ties)
-{
-    const int lane = threadIdx.x & 31;
-    uint32_t prefix = 0, mask = 0;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-#pragma unroll
-        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
-        __syncwarp();
-        for (int i = lane; i < cnt; i += 32) {
-            uint32_t w;
-            if (word(i, &w) && (w & mask) == prefix) atomicAdd(&hist[(w >> shift) & 255u], 1u);
-        }
-        __syncwarp();
-        uint32_t local[8];
-        uint32_t tot = 0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { local[b] = hist[lane * 8 + b]; tot += local[b]; }
-        uint32_t suf = tot;  // inclusive suffix sum over lanes (high digits first)
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t v = __shfl_down_sync(0xffffffffu, suf, off);
-            if (lane + off < 32) suf += v;
-        }
-        uint32_t above = suf - tot;
-        bool mine = (above < (uint32_t)want) && ((uint32_t)want <= suf);
-        uint32_t digit = 0, nw = 0;
-        if (mine) {
-            uint32_t c = above;
-#pragma unroll
-            for (int b = 7; b >= 0; --b) {
-                if (c < (uint32_t)want && (uint32_t)want <= c + local[b]) { digit = lane * 8 + b; nw = want - c; }
-                c += local[b];
-            }
-        }
-        uint32_t who = __ballot_sync(0xffffffffu, mine);
-        int src = who ? (__ffs(who) - 1) : 0;
-        digit = __shfl_sync(0xffffffffu, digit, src);
-        nw = __shfl_sync(0xffffffffu, nw, src);
-        prefix |= digit << shift;
-        mask |= 255u << shift;
-        want = (int)nw;
-        __syncwarp();
-    }
-    *rank_in_ties = want;
-    return prefix;
 }
 
 }  // namespace sr

@@ -3,29 +3,36 @@
 // cublasSgemv + computeNormsKernel + normalizeSimilaritiesKernel + D2H + host
 // heap, Recommender.cu:184-254 and :293-315, for a whole batch of queries).
 //
-// Work = (query tile x song tile) units dealt in contiguous runs to a persistent
-// grid.  Per song tile every thread keeps S songs of the PRE-NORMALISED store in
-// registers (as S/2 packed pairs) and walks the query tile held in shared memory:
+// Work = (query tile x song tile) units on a persistent grid: a CTA serves one query tile
+// (<= 256 queries, state in shared memory) and claims song tiles from a per-query-tile counter
+// (DYN shapes) or walks a contiguous run of units (static shapes).  Per song tile every thread
+// keeps S songs of the PRE-NORMALISED store in registers (as S/2 packed pairs), loaded straight
+// from global memory or, in the small-batch shape, staged through shared memory by TMA:
 //
 //   filter (hot, 12 FMA per pair, issued as FFMA2 = two songs per instruction; the
 //   query value is a UNIFORM-register scalar operand fed from constant memory, so an
 //   FFMA2 reads only the song pair and the accumulator pair from the register file
 //   -- measured on B200 this is what lifts the loop from ~70% to >85% of the FP32 pipe):
-//       acc = -T' + sum_j fhat_j * qhat_j        T' = (exact running K-th best) - kEps
+//       acc = -T' + sum_j fhat_j * qhat_j        T' = (best known bound of the K-th best) - kEps
 //     sign(acc) == 0  <=>  the pair MAY belong to the exact top-K  (DESIGN.md
 //     "filter slack": |acc - (oracle score - T')| < kEps for regular rows; NaN
-//     rows/queries always pass).  One LOP3 tree over the sign bits per S songs.
-//   hit (rare): the song id is appended, unscored, to the query's candidate buffer.
+//     rows/queries always pass).  One LOP3 tree over the sign bits per S songs, one bit
+//     per query in a mask: the loop is branch-free.
+//   hit (rare): picked up after every 32 queries; the filter is re-run for the flagged query
+//     and the song id is appended, unscored, to the query's hit buffer (shared memory).
 //   settle (rare, warp-cooperative, at tile borders): pending ids are scored in the
 //     reference's own arithmetic (Recommender.cu:263-271, unfused mul/add, sqrt*qn, IEEE
 //     divide, clamp) from the RAW store and merged into this CTA's exact top-K list of the
-//     query (shared memory; score desc, id asc).  A full list's K-th key is a lower bound of
-//     the final K-th best; it raises T' and is published to the other CTAs working on the
-//     same queries (g_best, atomicMax -- no locks anywhere).
-//   flush: at the end of its run over a query tile the CTA appends its lists to the
-//     per-query pool; finalize_kernel merges the pool into the ordered top-K.
-//   rescan (pathological tiles only: mass ties, NaN queries): when a tile yields
-//     more hits than the buffer holds, the owning warp scores the tile exactly.
+//     query (shared memory; score desc, id asc).  Threshold feedback is lock-free: a full
+//     list's K-th key, and the smallest of the query's K global residue slots (gslot,
+//     atomicMax of every exact key into slot id mod K: K distinct songs), are lower bounds of
+//     the final K-th best; the better one raises T' and is published (g_best, atomicMax).
+//   overflow: when a tile yields more hits than the buffer holds (clustered stores), the
+//     buffered hits raise the threshold and the CTA re-filters the tile against it; if the
+//     threshold did not move (mass ties, NaN queries) the owning warp scores the tile exactly.
+//   flush: after its last tile of a query tile the CTA appends the list entries that can
+//     still matter to the per-query pool; finalize_kernel merges the pool into the ordered top-K.
+//   bound pass (bound_kernel, before the scan): starting thresholds at filter speed.
 //
 // The filter only ever discards pairs that provably are not in the exact top-K,
 // so results are bit-identical to the oracle whatever the thresholds were.
@@ -47,7 +54,7 @@ struct ScanArgs {
     int64_t n;               // valid local rows
     int32_t id_base;         // global id of local row 0
     int n_tiles;             // song tiles this launch visits ...
-    int tile_stride;         // ... tile t of the launch is store tile t * tile_stride (pilot passes sample)
+    int tile_stride;         // ... tile t of the launch is store tile t * tile_stride (1: every tile)
     int upc, extra;          // work units per CTA: CTA b owns upc + (b < extra) units, in order
     int cpq;                 // DYN shapes: CTAs per query tile (the first grid - cpq*nqt tiles get one more)
     int *tile_ctr;           // DYN shapes: [nqt] next unclaimed song tile of each query tile
