@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 const int qe = min(32, nql - qb);
                 uint32_t mask = 0;
                 if (DEFER) {
-#pragma unroll 4
+#pragma unroll 16
                     for (int i = 0; i < qe; ++i) {
                         float2 acc[S / 2];
                         const uint32_t m = filter_query<S>(fp, q0 + qb + i, c.nthr[qb + i], acc);
