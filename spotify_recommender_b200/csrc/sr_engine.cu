@@ -361,12 +361,13 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->excl, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gbest, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->gbound, (size_t)nq * nblk * 4))) return rc;
-    if ((rc = ensure(e, e->gslot, (size_t)nq * K * 8))) return rc;
+    const int nslot = std::max(256, (K + 31) / 32 * 32);  // residue slots per query (global threshold feedback)
+    if ((rc = ensure(e, e->gslot, (size_t)nq * nslot * 4))) return rc;
     if ((rc = ensure(e, e->tile_ctr, (size_t)(nqt + 1) * 4))) return rc;
     if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->pool, (size_t)nq * segs * K * 8))) return rc;
 
-    SR_CUDA(cudaMemsetAsync(e->gslot.p, 0, (size_t)nq * K * 8, st));
+    SR_CUDA(cudaMemsetAsync(e->gslot.p, 0, (size_t)nq * nslot * 4, st));
     if (use_bound) SR_CUDA(cudaMemsetAsync(e->gbound.p, 0, (size_t)nq * nblk * 4, st));
     {
         PrepArgs p;
@@ -407,7 +408,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.K = K; a.cap = cap; a.settle_at = e->settle_at > 0 ? std::min(e->settle_at, cap) : std::max(4, cap / 16);
         a.refresh_every = std::max(1, std::min(8, 64 / qt));
         a.trigger_at = e->trigger_at > 0 ? std::min(std::max(e->trigger_at, a.settle_at), cap) : std::max(a.settle_at, cap / 2);
-        a.gslot = (uint64_t *)e->gslot.p + (size_t)g0 * K;
+        a.gslot = (uint32_t *)e->gslot.p + (size_t)g0 * nslot;
+        a.nslot = nslot;
         a.pool = (uint64_t *)e->pool.p + (size_t)g0 * segs * K; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
         a.segs = segs;
         a.g_best = (uint32_t *)e->gbest.p + g0;

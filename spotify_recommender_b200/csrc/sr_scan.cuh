@@ -24,9 +24,10 @@
 //     reference's own arithmetic (Recommender.cu:263-271, unfused mul/add, sqrt*qn, IEEE
 //     divide, clamp) from the RAW store and merged into this CTA's exact top-K list of the
 //     query (shared memory; score desc, id asc).  Threshold feedback is lock-free: a full
-//     list's K-th key, and the smallest of the query's K global residue slots (gslot,
-//     atomicMax of every exact key into slot id mod K: K distinct songs), are lower bounds of
-//     the final K-th best; the better one raises T' and is published (g_best, atomicMax).
+//     list's K-th key, and the K-th largest of the query's global residue slots (gslot:
+//     atomicMax of every exact score into slot id mod nslot, i.e. the bests of nslot disjoint
+//     sets of songs), are lower bounds of the final K-th best; the better one raises T' and is
+//     published (g_best, atomicMax).
 //   overflow: when a tile yields more hits than the buffer holds (clustered stores), the
 //     buffered hits raise the threshold and the CTA re-filters the tile against it; if the
 //     threshold did not move (mass ties, NaN queries) the owning warp scores the tile exactly.
@@ -74,8 +75,9 @@ struct ScanArgs {
     int32_t *pool_cnt;       // [nq] keys in the pool slab
     int segs;                // slab capacity in segments (scan_segs())
     uint32_t *g_best;        // [nq] orderable score: best known lower bound of the final K-th best
-    uint64_t *gslot;         // [nq][K] lock-free global feedback: slot (id mod K) holds the best exact
-                             // key any CTA has found among the songs with that residue (atomicMax)
+    uint32_t *gslot;         // [nq][nslot] lock-free global feedback: slot (id mod nslot) holds the best exact
+                             // score (orderable) any CTA has found among the songs with that residue
+    int nslot;               // >= K, multiple of 32
     unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] inserts
 };
 
@@ -293,25 +295,42 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
             const int i = base + r * 32 + lane;
             key[r] = (i < cnt) ? exact_key(a, (int64_t)hit[i] - a.id_base, q, qn, ex) : 0ull;
             if (key[r] < floor_key) key[r] = 0ull;
-            if (key[r]) atomicMax((unsigned long long *)(a.gslot + (size_t)c.qid[ql] * a.K + key_id(key[r]) % (uint32_t)a.K), (unsigned long long)key[r]);
+            if (key[r]) atomicMax(a.gslot + (size_t)c.qid[ql] * a.nslot + key_id(key[r]) % (uint32_t)a.nslot, (uint32_t)(key[r] >> 32));
         }
         kth = list_merge4(a, c, ql, key);
     }
     // A full list's minimum is this CTA's exact K-th best.  Global feedback without locks: the
-    // K residue slots hold K distinct songs, so the smallest slot key is a lower bound of the
-    // K-th best over everything ANY CTA has scored so far -- much tighter than this CTA's own
-    // K-th best when many CTAs share a query.  The better of the two is published.
+    // residue slots hold the best scores of nslot DISJOINT sets of songs, found by any CTA, so
+    // the K-th largest slot value is a lower bound of the K-th best over everything scored so
+    // far by anyone -- with nslot >= 2.5 K it is close to that K-th best itself, and far
+    // tighter than this CTA's own view when 37 CTAs share a query.  The better of the two bounds
+    // is published.  (K-th largest by binary search over the 32 bits of the orderable scores.)
     auto publish = [&](uint64_t kth_key) {
-        uint64_t slot_min = ~0ull;
-        const uint64_t *slots = a.gslot + (size_t)c.qid[ql] * a.K;
-        for (int i = lane; i < a.K; i += 32) {
-            const uint64_t v = __ldcg(slots + i);
-            slot_min = v < slot_min ? v : slot_min;
+        const uint32_t *slots = a.gslot + (size_t)c.qid[ql] * a.nslot;
+        uint32_t sv[8];
+        const int per_lane = a.nslot / 32;  // <= 8 on the register path
+        uint32_t slot_kth = 0;
+        if (per_lane <= 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sv[j] = (j < per_lane) ? __ldcg(slots + j * 32 + lane) : 0u;
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint32_t cand = slot_kth | (1u << bit);
+                int cgt = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cgt += (sv[j] >= cand);
+                if ((int)__reduce_add_sync(0xffffffffu, (unsigned)cgt) >= a.K) slot_kth = cand;
+            }
+        } else {
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint32_t cand = slot_kth | (1u << bit);
+                int cgt = 0;
+                for (int i = lane; i < a.nslot; i += 32) cgt += (__ldcg(slots + i) >= cand);
+                if ((int)__reduce_add_sync(0xffffffffu, (unsigned)cgt) >= a.K) slot_kth = cand;
+            }
         }
-        slot_min = warp_min_u64(slot_min);  // 0 while some slot is still empty
         if (lane == 0) {
             uint32_t b = __ldcg(a.g_best + c.qid[ql]);
-            const uint32_t mine = max((uint32_t)(kth_key >> 32), (uint32_t)(slot_min >> 32));
+            const uint32_t mine = max((uint32_t)(kth_key >> 32), slot_kth);
             if (mine > b) {
                 atomicMax(a.g_best + c.qid[ql], mine);
                 b = mine;
@@ -337,7 +356,7 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
                     const int64_t row = base + r * 32 + lane;
                     key[r] = (row < tile_hi) ? exact_key(a, row, q, qn, ex) : 0ull;
                     if (key[r] < floor_key) key[r] = 0ull;
-                    if (key[r]) atomicMax((unsigned long long *)(a.gslot + (size_t)c.qid[ql] * a.K + key_id(key[r]) % (uint32_t)a.K), (unsigned long long)key[r]);
+                    if (key[r]) atomicMax(a.gslot + (size_t)c.qid[ql] * a.nslot + key_id(key[r]) % (uint32_t)a.nslot, (uint32_t)(key[r] >> 32));
                 }
                 kth = list_merge4(a, c, ql, key);
             }
