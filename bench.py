@@ -167,6 +167,11 @@ def run_reference(args) -> None:
 
 
 def run_ours(args) -> None:
+    global BATCH, TOPK
+    if args.batch:
+        BATCH = args.batch
+    if args.topk:
+        TOPK = args.topk
     import torch
     import torch.distributed as dist
     from spotify_recommender_b200 import synth
@@ -187,7 +192,7 @@ def run_ours(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_total = SONGS_PER_GPU * world
+    n_total = int(args.songs_total) if args.songs_total else SONGS_PER_GPU * world
     eng = Engine(local_rank)
     if args.variant is not None:
         eng.set_option("variant", args.variant)
@@ -324,9 +329,9 @@ def run_ours(args) -> None:
             "metric": METRIC, "value": value, "unit": "song-pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{SONGS_PER_GPU} songs x 12 features per GPU ({n_total} total, row-sharded), "
+            "config": {"workload": f"{hi - lo} songs x 12 features per GPU ({n_total} total, row-sharded), "
                                    f"batch of {BATCH} in-store queries, exact top-{TOPK}",
-                       "songs_total": n_total, "songs_per_gpu": SONGS_PER_GPU, "queries_per_batch": BATCH,
+                       "songs_total": n_total, "songs_per_gpu": hi - lo, "queries_per_batch": BATCH,
                        "top_k": TOPK, "parallelism": f"row-shard x{world}" + (" + NCCL all-gather + merge" if world > 1 else ""),
                        "l2": "store (2 x 480 MB per GPU) is larger than the 126 MB L2; every step uses a fresh query batch",
                        "kernel_shape": variant_names()[eng.stat("variant")]},
@@ -355,6 +360,10 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--variant", type=int, default=None, help="scan kernel shape (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--songs-total", type=float, default=None,
+                    help="non-contract runs: total songs, row-sharded over the GPUs (e.g. 1e8 for BASELINE config 4)")
+    ap.add_argument("--batch", type=int, default=None, help="non-contract runs: queries per batch")
+    ap.add_argument("--topk", type=int, default=None, help="non-contract runs: K")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
