@@ -63,9 +63,24 @@ def build_recommender(force: bool = False) -> str:
     return RECOMMENDER_SO
 
 
+CLI_BIN = os.path.join(PKG, "sr_recommend")
+
+
+def build_cli(force: bool = False) -> str:
+    """The batch CLI (csrc/sr_cli.cpp) on the C++ Recommender class."""
+    src = os.path.join(CSRC, "sr_cli.cpp")
+    if force or _stale(CLI_BIN, engine_sources()):
+        build_recommender(force)
+        cmd = ["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", CLI_BIN, src,
+               "-L", PKG, "-lsr_recommender", "-lsr_engine", "-Wl,-rpath,$ORIGIN"]
+        subprocess.check_call(cmd)
+    return CLI_BIN
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_engine(force, verbose)
     build_recommender(force)
+    build_cli(force)
 
 
 if __name__ == "__main__":

@@ -736,7 +736,7 @@ template <int S, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) bound_kernel(const ScanArgs a, int nblk, int n_sample, int stride,
                                                               uint32_t *gmax)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *s_max = reinterpret_cast<uint32_t *>(smem_raw);  // [qt][nblk] orderable block maxima of this unit
     const int tid = threadIdx.x;
     const int blk = (tid % kLT) % nblk;

@@ -141,6 +141,25 @@ def test_reference_cli_end_to_end(tmp_path):
     assert rec.find_id(want[0]) == rec.find_name("Track 500")
     assert all(rec.find_id(w) == int(g) for w, g in zip(want[1:], got))
     rec.close()
+    # the batch CLI on the same file: --ids, --range, CSV out
+    from spotify_recommender_b200 import build
+    cli = build.CLI_BIN
+    (tmp_path / "ids.txt").write_text("id0000500\nid0001234\n")
+    r = subprocess.run([cli, "--data", "songs_data.bin", "--ids", "ids.txt", "-n", "5", "--out", "recs.csv"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split(",") for l in (tmp_path / "recs.csv").read_text().splitlines()[1:]]
+    assert len(rows) == 10
+    _, want5, _ = ids(cpu, "--id", "id0000500", "-n", "5")
+    rec3 = HostRecommender.from_file(str(tmp_path / "songs_data.bin"))
+    assert [int(x[2]) for x in rows[:5]] == [rec3.find_id(w) for w in want5[1:]]
+    rec3.close()
+    sims = [float(x[3]) for x in rows[:5]]
+    assert sims == sorted(sims, reverse=True) and all(-1.0 <= s <= 1.0 for s in sims)
+    r = subprocess.run([cli, "--data", "songs_data.bin", "--range", "10", "14", "-n", "3"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and len(r.stdout.splitlines()) == 1 + 4 * 3
+    assert subprocess.run([cli, "--data", "songs_data.bin", "--ids", "missing.txt"], cwd=tmp_path).returncode == 1
     bad = tmp_path / "truncated.bin"
     bad.write_bytes((tmp_path / "songs_data.bin").read_bytes()[:100_000])
     with pytest.raises(RuntimeError):
