@@ -27,4 +27,4 @@ bad = np.where((wi != ref[0][sel]).any(axis=1))[0]
 print("vs oracle: mismatching rows", bad.size, "of", sel.size)
 for b in bad[:5]:
     print("  q", sel[b], q[sel[b]], "got", ref[0][sel[b]], "want", wi[b], ref[1][sel[b]], ws[b])
-print("stats: hits", e.stat("filter_hits"), "settles", e.stat("settles"), "rescans", e.stat("rescans"), "inserts", e.stat("inserts"))
+print("stats: hits", e.stat("filter_hits"), "settles", e.stat("settles"), "rescans", e.stat("rescans"), "refilters", e.stat("refilters"))
