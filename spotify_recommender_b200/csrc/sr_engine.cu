@@ -72,18 +72,15 @@ struct Variant {
 #define SR_VARIANT_DYN(S, T, M) \
     {"S" #S "xT" #T "x" #M "-dyn", S, T, M, false, true, launch_scan<S, T, M, true, false, true>, occ_scan<S, T, M, true, false, true>, launch_bound<S, T, M>}
 const Variant kVariants[] = {
-    SR_VARIANT(8, 256, 2, false),
-    SR_VARIANT(8, 256, 2, true),
-    SR_VARIANT(8, 512, 1, false),
-    SR_VARIANT(8, 512, 1, true),
-    SR_VARIANT(4, 256, 4, true),
-    SR_VARIANT_TMA(8, 256, 1),
-    SR_VARIANT_TMA(8, 256, 2),
-    SR_VARIANT_DYN(8, 512, 1),
-    SR_VARIANT_DYN(8, 256, 2),
+    SR_VARIANT(8, 256, 2, false),   // 0  plain hit branch in the loop
+    SR_VARIANT(8, 256, 2, true),    // 1  branch-free loop, deferred hits
+    SR_VARIANT(8, 512, 1, false),   // 2
+    SR_VARIANT(8, 512, 1, true),    // 3  static runs of units (fallback of 5 when query tiles outnumber CTAs)
+    SR_VARIANT_TMA(8, 256, 2),      // 4  small batches: TMA-staged tiles
+    SR_VARIANT_DYN(8, 512, 1),      // 5  large batches: dynamic tile claiming
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-constexpr int kAutoSmall = 6, kAutoLarge = 7, kStaticLarge = 3, kAutoS = 8;
+constexpr int kAutoSmall = 4, kAutoLarge = 5, kStaticLarge = 3, kAutoS = 8;
 
 enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kBound, kNumKernels };
 const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge", "bound"};
