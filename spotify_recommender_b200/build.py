@@ -43,7 +43,8 @@ def engine_sources() -> list[str]:
 
 def build_engine(force: bool = False, verbose: bool = False) -> str:
     if force or _stale(ENGINE_SO, engine_sources()):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-o", ENGINE_SO, os.path.join(CSRC, "sr_engine.cu")]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("SR_NVCC_EXTRA", "").split(),  # e.g. -DSR_SCAN_TIMING (development)
+               "-o", ENGINE_SO, os.path.join(CSRC, "sr_engine.cu")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

@@ -341,7 +341,9 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         const int64_t gunits = (int64_t)((std::min(gsize, nq - g0) + qt - 1) / qt) * n_tiles;
         upc_min = (int)std::min<int64_t>(upc_min, std::max<int64_t>(1, gunits / std::min<int64_t>(grid, gunits)));
     }
-    const int segs = std::max(scan_segs(n_tiles, upc_min), grid / std::max(1, nqt) + 3);
+    // (dynamic shapes: a query tile's home CTAs plus the late joiners it admits)
+    const int steal_max = std::min(grid, 16);
+    const int segs = std::max(scan_segs(n_tiles, upc_min), grid / std::max(1, nqt) + 3 + (v.dynamic ? steal_max : 0));
 
     // threshold bootstrap: the bound pass (filter speed, per query group) when the store has
     // enough full tiles, else the exact sample
@@ -360,7 +362,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->gbound, (size_t)nq * nblk * 4))) return rc;
     const int nslot = std::max(256, (K + 31) / 32 * 32);  // residue slots per query (global threshold feedback)
     if ((rc = ensure(e, e->gslot, (size_t)nq * nslot * 4))) return rc;
-    if ((rc = ensure(e, e->tile_ctr, (size_t)(nqt + 1) * 4))) return rc;
+    if ((rc = ensure(e, e->tile_ctr, (size_t)(nqt + 1) * 8))) return rc;
     if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->pool, (size_t)nq * segs * K * 8))) return rc;
 
@@ -442,11 +444,13 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             a.extra = (int)(gunits % ggrid);
             a.cpq = 0;
             a.tile_ctr = (int *)e->tile_ctr.p;
+            a.visit_ctr = a.tile_ctr + gnqt;
+            a.steal_max = steal_max;
             const Variant *vl = &v;
             if (v.dynamic && gnqt > ggrid) vl = &kVariants[kStaticLarge];  // more query tiles than CTAs: static runs (same S, threads, smem)
             if (vl->dynamic) {
                 a.cpq = ggrid / gnqt;
-                SR_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, (size_t)gnqt * 4, st));
+                SR_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, (size_t)gnqt * 8, st));
             }
             Scope sc(e, st, kScan);
             SR_CUDA(vl->launch(a, ggrid, smem, st));
@@ -779,8 +783,9 @@ int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value)
 {
     if (!e || !key || !value) return SR_EINVAL;
     SR_CUDA(cudaSetDevice(e->device));
-    static const char *const dev_keys[] = {"filter_hits", "settles", "rescans", "rescored", "refilters"};
-    for (int i = 0; i < 5; ++i) {
+    static const char *const dev_keys[] = {"filter_hits", "settles", "rescans", "rescored", "refilters",
+                                           "hot_cycles", "settle_cycles", "cta_cycles"};  // last three: -DSR_SCAN_TIMING builds only
+    for (int i = 0; i < 8; ++i) {
         if (!strcmp(key, dev_keys[i])) {
             unsigned long long h[8];
             SR_CUDA(cudaStreamSynchronize(e->stream));

@@ -59,6 +59,8 @@ struct ScanArgs {
     int upc, extra;          // work units per CTA: CTA b owns upc + (b < extra) units, in order
     int cpq;                 // DYN shapes: CTAs per query tile (the first grid - cpq*nqt tiles get one more)
     int *tile_ctr;           // DYN shapes: [nqt] next unclaimed song tile of each query tile
+    int *visit_ctr;          // DYN shapes: [nqt] CTAs that joined a query tile after finishing their own
+    int steal_max;           // DYN shapes: how many such late joiners a query tile admits (sizes the pool slab)
     const float *qraw;       // [nq][12] raw query rows            (all per-query arrays are
     const float *qn;         // [nq] exact query norms               already offset to the first
     const int32_t *exclude;  // [nq] global id to skip or -1         query of this group)
@@ -102,6 +104,10 @@ __device__ __forceinline__ void tma_load_tile(void *dst, const void *src, uint32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -392,6 +398,16 @@ __host__ __device__ __forceinline__ int64_t hat_offset(int64_t row, int j, int S
 }
 
 // One filter pass of a thread's S songs against query record `ql` of the tile.
+// Development instrumentation (-DSR_SCAN_TIMING): thread 0 of every CTA accumulates the clock
+// cycles it spends in the hot loop / in settle phases / in the kernel into stats[5..7].
+#ifdef SR_SCAN_TIMING
+#define SR_TIME_BEGIN(slot) do { if (threadIdx.x == 0) s_time[3] = (int)clock(); } while (0)
+#define SR_TIME_END(slot) do { if (threadIdx.x == 0) s_time[slot] += (int)clock() - s_time[3]; } while (0)
+#else
+#define SR_TIME_BEGIN(slot) do { } while (0)
+#define SR_TIME_END(slot) do { } while (0)
+#endif
+
 template <int S>
 __device__ __forceinline__ uint32_t filter_query(const float2 (&fp)[S / 2][kF], int cq, float nt, float2 (&acc)[S / 2])
 {
@@ -453,9 +469,18 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     int *s_flag = reinterpret_cast<int *>(c.hit + (size_t)a.qt * a.cap);
     int *s_redo_cnt = s_flag + 4;                 // [2]
     int *s_redo = s_redo_cnt + 4;                 // [2][qt] queries whose tile must be re-filtered
-    int *s_next = s_redo + 2 * a.qt;              // [2] DYN: claimed song tiles (this one / the next)
+    int *s_next = s_redo + 2 * a.qt;              // DYN: [0..2] claimed song tiles (this one and the next two), [3] next query tile
+    // DYN: the per-tile barrier is split (arrive ... wait) so the next tile's loads overlap the wait
+    __shared__ uint64_t s_tbar;
+    uint32_t tbar_phase = 0;
     if (threadIdx.x < 4) s_flag[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_redo_cnt[threadIdx.x] = 0;
+#ifdef SR_SCAN_TIMING
+    __shared__ int s_time[4];  // hot loop, settle phases, (unused), scratch
+    __shared__ long long s_t0;
+    if (threadIdx.x < 4) s_time[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_t0 = clock64();
+#endif
     int tphase = 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -465,14 +490,18 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     int u = (int)blockIdx.x * a.upc + min((int)blockIdx.x, a.extra);
     int u_end = u + a.upc + ((int)blockIdx.x < a.extra ? 1 : 0);
     int qtile = 0, t0 = u;
+    const int nqt_d = (a.nq + a.qt - 1) / a.qt;
     if (DYN) {
-        // one segment: the query tile this CTA serves (uniform arithmetic again)
-        const int nqt_d = (a.nq + a.qt - 1) / a.qt;
+        // first segment: this CTA's home query tile (uniform arithmetic again)
         int bb = (int)blockIdx.x;
         if (bb >= a.cpq * nqt_d) qtile = bb - a.cpq * nqt_d;
         else while (bb >= a.cpq) { bb -= a.cpq; ++qtile; }
         u = 0; u_end = 1; t0 = 0;
-        if (tid == 0) s_next[0] = atomicAdd(a.tile_ctr + qtile, 1);
+        if (tid == 0) {
+            s_next[0] = atomicAdd(a.tile_ctr + qtile, 1);
+            s_next[1] = atomicAdd(a.tile_ctr + qtile, 1);
+            mbar_init(&s_tbar, WARPS);
+        }
     } else {
         while (t0 >= a.n_tiles) { t0 -= a.n_tiles; ++qtile; }
     }
@@ -505,19 +534,36 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         for (int i = tid; i < nql * kF; i += THREADS) c.qraw[i] = a.qraw[(size_t)q0 * kF + i];
         __syncthreads();
 
-        int it = 0;
+        int it = 0, slot = 0;
+        // this thread's S songs of store tile `t` -> registers: S/2 interleaved pairs, six 128-bit
+        // loads each, every load two ready FFMA2 operands
+        float2 fp[S / 2][kF];
+        auto load_songs = [&](int t) {
+            const int64_t lt = (int64_t)t * a.tile_stride * SUB + tid / kLT;
+            const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (lt * (S / 2) * kLT + tid % kLT) * 6;
+#pragma unroll
+            for (int p = 0; p < S / 2; ++p) {
+#pragma unroll
+                for (int c4 = 0; c4 < 6; ++c4) {
+                    const float4 v = __ldg(src + (int64_t)p * kLT * 6 + c4);
+                    fp[p][2 * c4] = make_float2(v.x, v.y);
+                    fp[p][2 * c4 + 1] = make_float2(v.z, v.w);
+                }
+            }
+        };
         // (redux.sync hands the claimed index back as a warp-uniform value, which keeps the tile loop --
         // and with it the hot loop's uniform-register operands -- in uniform control flow)
-        for (int tile = DYN ? __reduce_max_sync(0xffffffffu, s_next[0]) : t0; tile < t1;
-             ++it, tile = DYN ? __reduce_max_sync(0xffffffffu, s_next[it & 1]) : tile + 1) {
-            if (DYN && tid == 0) s_next[(it + 1) & 1] = atomicAdd(a.tile_ctr + qtile, 1);  // read after this tile's barrier
+        // DYN claims two tiles ahead through three slots: the slot written during tile t was last
+        // read during tile t-2, and the NEXT tile's index is already visible while tile t runs, so
+        // its songs are loaded between arriving at tile t's barrier and waiting on it.
+        int tile = DYN ? __reduce_max_sync(0xffffffffu, s_next[0]) : t0;
+        if (DYN) load_songs(min(tile, a.n_tiles - 1));
+        for (; tile < t1; ++it, slot = (slot == 2 ? 0 : slot + 1)) {
+            if (DYN && tid == 0) s_next[slot == 0 ? 2 : slot - 1] = atomicAdd(a.tile_ctr + qtile, 1);
             const int64_t stile = (int64_t)tile * a.tile_stride;  // store tile
             const int64_t ltile = stile * SUB + tid / kLT;      // this thread's layout tile
             const int row0 = (int)(ltile * (S * kLT)) + tid % kLT;  // its songs: row0 + s * kLT (ids are 32-bit)
 
-            // ---- S songs of the normalised store into registers: S/2 interleaved pairs,
-            // six 128-bit loads each, every load two ready FFMA2 operands
-            float2 fp[S / 2][kF];
             if (STAGE) {
                 mbar_wait(s_bar, sphase);  // this tile has landed in shared memory
                 sphase ^= 1u;
@@ -538,17 +584,8 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     else if (u + (t1 - t0) < u_end) nxt = 0;
                     if (nxt >= 0) tma_load_tile(s_tile, a.hat + nxt * (TS * kF), kTileBytes, s_bar);
                 }
-            } else {
-                const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (ltile * (S / 2) * kLT + tid % kLT) * 6;
-#pragma unroll
-                for (int p = 0; p < S / 2; ++p) {
-#pragma unroll
-                    for (int c4 = 0; c4 < 6; ++c4) {
-                        const float4 v = __ldg(src + (int64_t)p * kLT * 6 + c4);
-                        fp[p][2 * c4] = make_float2(v.x, v.y);
-                        fp[p][2 * c4 + 1] = make_float2(v.z, v.w);
-                    }
-                }
+            } else if (!DYN) {
+                load_songs(tile);
             }
 
             // a settle phase follows this tile if some hit buffer fills up (flagged by the thread
@@ -579,6 +616,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             // are picked up after every 32 queries by re-running the filter for the flagged
             // queries, so the FFMA2 stream of consecutive queries is never split by a branch
             // and every operand that depends on the query stays in uniform registers.
+            SR_TIME_BEGIN(0);
             for (int qb = 0; qb < nql; qb += 32) {
                 const int qe = min(32, nql - qb);
                 uint32_t mask = 0;
@@ -606,6 +644,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     append(ql, acc);
                 }
             }
+            SR_TIME_END(0);
             // ---- tile epilogue: warp w looks after queries ql == w (mod WARPS), one lane each:
             // adopt thresholds published by other CTAs and settle hit buffers that filled up -- every non-empty
             // one after a segment's first and last tile.  One barrier when there is nothing to
@@ -621,11 +660,22 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     }
                 }
             }
-            __syncthreads();  // all hits of this tile are in the buffers
+            int next_tile = tile + 1;
+            if (DYN) {
+                next_tile = __reduce_max_sync(0xffffffffu, s_next[slot == 2 ? 0 : slot + 1]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_tbar);
+                load_songs(min(next_tile, a.n_tiles - 1));  // in flight while the slower warps finish
+                mbar_wait(&s_tbar, tbar_phase);
+                tbar_phase ^= 1u;
+            } else {
+                __syncthreads();  // all hits of this tile are in the buffers
+            }
             const bool settle_phase = forced || (s_flag[tphase] != 0);
             if (tid == 0) s_flag[tphase == 0 ? 2 : tphase - 1] = 0;  // the previous tile's slot
             tphase = (tphase == 2) ? 0 : tphase + 1;
             if (settle_phase) {
+                SR_TIME_BEGIN(1);
                 bool need = false;
                 {
                     const int ql_mine = warp + WARPS * lane;
@@ -678,7 +728,11 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     }
                     __syncthreads();
                 }
+                // (the prefetched songs were not kept alive across the settle code: fetch them again, L2-hot)
+                if (DYN) load_songs(min(next_tile, a.n_tiles - 1));
+                SR_TIME_END(1);
             }
+            tile = next_tile;
         }
         if (DYN) {  // the last tile is not known in advance: settle whatever is still pending now
             bool need = false;
@@ -714,12 +768,40 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             }
         }
         __syncthreads();
-        u += (t1 - t0);
-        t0 = 0;
-        ++qtile;
+        if (DYN) {
+            // this query tile has no unclaimed song tiles left: join another one that has (CTAs
+            // per query tile rarely divide the grid evenly, and settle work differs between tiles)
+            if (tid == 0) {
+                int cand = -1, c2 = qtile;
+                for (int k = 1; k < nqt_d && cand < 0; ++k) {
+                    c2 = (c2 + 1 == nqt_d) ? 0 : c2 + 1;
+                    if (*(volatile int *)(a.tile_ctr + c2) < a.n_tiles && atomicAdd(a.visit_ctr + c2, 1) < a.steal_max) cand = c2;
+                }
+                s_next[3] = cand;
+                if (cand >= 0) {
+                    s_next[0] = atomicAdd(a.tile_ctr + cand, 1);
+                    s_next[1] = atomicAdd(a.tile_ctr + cand, 1);
+                }
+            }
+            __syncthreads();
+            const int cand = __reduce_max_sync(0xffffffffu, s_next[3]);
+            if (cand < 0) break;
+            qtile = cand;
+        } else {
+            u += (t1 - t0);
+            t0 = 0;
+            ++qtile;
+        }
     }
     __syncthreads();
     if (a.stats && tid == 0 && s_flag[3]) atomicAdd(a.stats + 0, (unsigned long long)s_flag[3]);
+#ifdef SR_SCAN_TIMING
+    if (a.stats && tid == 0) {
+        atomicAdd(a.stats + 5, (unsigned long long)(unsigned)s_time[0]);
+        atomicAdd(a.stats + 6, (unsigned long long)(unsigned)s_time[1]);
+        atomicAdd(a.stats + 7, (unsigned long long)(clock64() - s_t0));
+    }
+#endif
 }
 
 // ---- bound pass ---------------------------------------------------------------------------

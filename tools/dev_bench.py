@@ -46,3 +46,7 @@ for k in ks:
         print("k=%d %-18s scan %.3f ms/batch (%d launches) total %.3f ms  scan %.1f TFLOP/s = %.1f%% of 74.4; hits/q %.0f settles/q %.2f rescans %d rescored/q %.0f refilters %d" % (
             k, vname(v), ms / 2, cnt // 2, tot, tf, 100 * tf / 74.4, e.stat("filter_hits") / 2 / nq, e.stat("settles") / 2 / nq,
             e.stat("rescans"), e.stat("rescored") / 2 / nq, e.stat("refilters")), "| bound %.3f sample %.3f finalize %.3f prep %.3f" % (e.timing("bound")[0] / 2, e.timing("sample")[0] / 2, e.timing("finalize")[0] / 2, e.timing("prep")[0] / 2), flush=True)
+        if e.stat("cta_cycles"):
+            cta, hot, st = e.stat("cta_cycles"), e.stat("hot_cycles"), e.stat("settle_cycles")
+            print("   in-kernel cycles (thread 0 of every CTA): hot loop %.1f%%  settle phases %.1f%%  other (tile loads, barriers, prologue, flush) %.1f%%" % (
+                100.0 * hot / cta, 100.0 * st / cta, 100.0 * (cta - hot - st) / cta), flush=True)
