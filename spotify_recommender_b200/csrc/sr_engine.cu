@@ -119,7 +119,7 @@ struct sr_engine {
 
     // batch workspace (grow-only)
     DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, tile_ctr, pool_cnt, pool, out_idx, out_score, qin, exin;
-    unsigned long long *d_stats = nullptr;  // [8]
+    unsigned long long *d_stats = nullptr;  // [16]
     unsigned long long *d_irregular = nullptr;
     int32_t *d_flag = nullptr;
     void *h_pin = nullptr;
@@ -568,8 +568,8 @@ int sr_engine_create(sr_engine **out, int device)
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (err = cudaMalloc(&e->d_stats, 8 * 8)) != cudaSuccess || (err = cudaMalloc(&e->d_irregular, 8)) != cudaSuccess ||
-        (err = cudaMalloc(&e->d_flag, 4)) != cudaSuccess || (err = cudaMemset(e->d_stats, 0, 64)) != cudaSuccess ||
+        (err = cudaMalloc(&e->d_stats, 16 * 8)) != cudaSuccess || (err = cudaMalloc(&e->d_irregular, 8)) != cudaSuccess ||
+        (err = cudaMalloc(&e->d_flag, 4)) != cudaSuccess || (err = cudaMemset(e->d_stats, 0, 128)) != cudaSuccess ||
         (err = cudaMemset(e->d_flag, 0, 4)) != cudaSuccess) {
         int rc = fail(nullptr, SR_ECUDA, "engine setup: %s", cudaGetErrorString(err));
         sr_engine_destroy(e);
@@ -770,7 +770,7 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
         SR_CUDA(cudaStreamSynchronize(e->stream));
         int rc = resolve_timings(e);
         if (rc) return rc;
-        SR_CUDA(cudaMemset(e->d_stats, 0, 64));
+        SR_CUDA(cudaMemset(e->d_stats, 0, 128));
         e->launches = e->queries = 0;
         for (int i = 0; i < kNumKernels; ++i) { e->ms_total[i] = 0; e->ms_count[i] = 0; }
     } else {
@@ -784,12 +784,12 @@ int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value)
     if (!e || !key || !value) return SR_EINVAL;
     SR_CUDA(cudaSetDevice(e->device));
     static const char *const dev_keys[] = {"filter_hits", "settles", "rescans", "rescored", "refilters",
-                                           "hot_cycles", "settle_cycles", "cta_cycles"};  // last three: -DSR_SCAN_TIMING builds only
-    for (int i = 0; i < 8; ++i) {
+                                           "hot_cycles", "settle_cycles", "cta_cycles", "wait_cycles"};  // last four: -DSR_SCAN_TIMING builds only
+    for (int i = 0; i < 9; ++i) {
         if (!strcmp(key, dev_keys[i])) {
-            unsigned long long h[8];
+            unsigned long long h[16];
             SR_CUDA(cudaStreamSynchronize(e->stream));
-            SR_CUDA(cudaMemcpy(h, e->d_stats, 64, cudaMemcpyDeviceToHost));
+            SR_CUDA(cudaMemcpy(h, e->d_stats, 128, cudaMemcpyDeviceToHost));
             *value = (int64_t)h[i];
             return SR_OK;
         }

@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     if (threadIdx.x < 4) s_flag[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_redo_cnt[threadIdx.x] = 0;
 #ifdef SR_SCAN_TIMING
-    __shared__ int s_time[4];  // hot loop, settle phases, (unused), scratch
+    __shared__ int s_time[4];  // hot loop, settle phases, barrier wait, scratch
     __shared__ long long s_t0;
     if (threadIdx.x < 4) s_time[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_t0 = clock64();
@@ -559,7 +559,10 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         int tile = DYN ? __reduce_max_sync(0xffffffffu, s_next[0]) : t0;
         if (DYN) load_songs(min(tile, a.n_tiles - 1));
         for (; tile < t1; ++it, slot = (slot == 2 ? 0 : slot + 1)) {
-            if (DYN && tid == 0) s_next[slot == 0 ? 2 : slot - 1] = atomicAdd(a.tile_ctr + qtile, 1);
+            // (the claim for the tile after next: issued now, stored after the hot loop, so thread 0
+            // does not start every tile a global round trip late)
+            int claimed = 0;
+            if (DYN && tid == 0) claimed = atomicAdd(a.tile_ctr + qtile, 1);
             const int64_t stile = (int64_t)tile * a.tile_stride;  // store tile
             const int64_t ltile = stile * SUB + tid / kLT;      // this thread's layout tile
             const int row0 = (int)(ltile * (S * kLT)) + tid % kLT;  // its songs: row0 + s * kLT (ids are 32-bit)
@@ -650,7 +653,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             // one after a segment's first and last tile.  One barrier when there is nothing to
             // settle (threshold updates racing with other warps' reads are benign: any published
             // threshold is a valid lower bound), two when there is.
-            {
+            auto refresh = [&]() {
                 const int ql_mine = warp + WARPS * lane;
                 if (ql_mine < nql && it % a.refresh_every == 0) {
                     const uint32_t g = __ldcg(a.g_best + c.qid[ql_mine]);
@@ -659,16 +662,22 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                         c.nthr[ql_mine] = neg_threshold(g);
                     }
                 }
-            }
+            };
             int next_tile = tile + 1;
             if (DYN) {
+                if (tid == 0) s_next[slot == 0 ? 2 : slot - 1] = claimed;  // (claimed at the top of the tile)
                 next_tile = __reduce_max_sync(0xffffffffu, s_next[slot == 2 ? 0 : slot + 1]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_tbar);
-                load_songs(min(next_tile, a.n_tiles - 1));  // in flight while the slower warps finish
+                // in flight while the slower warps finish: the next tile's songs, the published thresholds
+                load_songs(min(next_tile, a.n_tiles - 1));
+                refresh();
+                SR_TIME_BEGIN(2);
                 mbar_wait(&s_tbar, tbar_phase);
+                SR_TIME_END(2);
                 tbar_phase ^= 1u;
             } else {
+                refresh();
                 __syncthreads();  // all hits of this tile are in the buffers
             }
             const bool settle_phase = forced || (s_flag[tphase] != 0);
@@ -800,6 +809,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         atomicAdd(a.stats + 5, (unsigned long long)(unsigned)s_time[0]);
         atomicAdd(a.stats + 6, (unsigned long long)(unsigned)s_time[1]);
         atomicAdd(a.stats + 7, (unsigned long long)(clock64() - s_t0));
+        atomicAdd(a.stats + 8, (unsigned long long)(unsigned)s_time[2]);
     }
 #endif
 }

@@ -47,6 +47,6 @@ for k in ks:
             k, vname(v), ms / 2, cnt // 2, tot, tf, 100 * tf / 74.4, e.stat("filter_hits") / 2 / nq, e.stat("settles") / 2 / nq,
             e.stat("rescans"), e.stat("rescored") / 2 / nq, e.stat("refilters")), "| bound %.3f sample %.3f finalize %.3f prep %.3f" % (e.timing("bound")[0] / 2, e.timing("sample")[0] / 2, e.timing("finalize")[0] / 2, e.timing("prep")[0] / 2), flush=True)
         if e.stat("cta_cycles"):
-            cta, hot, st = e.stat("cta_cycles"), e.stat("hot_cycles"), e.stat("settle_cycles")
-            print("   in-kernel cycles (thread 0 of every CTA): hot loop %.1f%%  settle phases %.1f%%  other (tile loads, barriers, prologue, flush) %.1f%%" % (
-                100.0 * hot / cta, 100.0 * st / cta, 100.0 * (cta - hot - st) / cta), flush=True)
+            cta, hot, st, wt = e.stat("cta_cycles"), e.stat("hot_cycles"), e.stat("settle_cycles"), e.stat("wait_cycles")
+            print("   in-kernel cycles (thread 0 of every CTA): hot loop %.1f%%  settle phases %.1f%%  tile barrier wait %.1f%%  other (prologue, flush, joins) %.1f%%; CTA-cycles/launch/SM %.0f" % (
+                100.0 * hot / cta, 100.0 * st / cta, 100.0 * wt / cta, 100.0 * (cta - hot - st - wt) / cta, cta / max(1, cnt) / 148), flush=True)
