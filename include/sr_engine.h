@@ -119,6 +119,7 @@ int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k,
  *   "batch"     max queries per internal pass (workspace is sized for it)
  *   "sample"    threshold-bootstrap sample size per query (0 = off, else power of two <= 4096)
  *   "hit_cap"   hit-buffer entries per query per CTA (multiple of 32; 0 = sized from k)
+ *   "bound_tiles" layout tiles (2048 songs each) sampled by the threshold bound pass (0 = auto: 48 for k <= 16, else 128)
  *   "trigger_at" a settle phase starts when some hit buffer holds this many ids (0 = cap / 2)
  *   "settle_at" ... and scores and merges every buffer holding at least this many (0 = cap / 16)
  *   "bound"     0: skip the bound pass (threshold bootstrap at filter speed)
@@ -149,6 +150,28 @@ int sr_engine_measure_fp32(sr_engine *e, int variant, double *tflops);
  * the one operation of the reference's scoring (Recommender.cu:271) that is not a
  * single hardware instruction on the GPU.  HOST buffers.  Used by the tests only. */
 int sr_engine_selftest_div(sr_engine *e, const float *a, const float *b, int n, float *out);
+
+/* SURVEY 8 f4 -- the min-max normalisation step of the reference's preprocessing
+ * (DataManager.cpp:270-301) on the GPU, deterministic and bit-identical to the reference's
+ * arithmetic: per column j < 11 of `raw11` (n x 11 row-major: danceability, energy, key,
+ * loudness, mode, speechiness, acousticness, instrumentalness, liveness, valence, tempo --
+ * DataManager.cpp:156-159) min and max over all rows (NaN never enters, as with std::min /
+ * std::max); out[i][j] = range > 1e-4f ? (x - min) / range : 0.5f; out[i][11] =
+ * (float)genre_id[i] / max(1, n_genres - 1).  `out` is n x 12, ready for
+ * sr_engine_load_features[_device]; `minmax` (22 floats: minima then maxima) may be NULL.
+ * A zero minimum / maximum counts as +0 whatever the order of signed zeros in the column.
+ * The _dev form takes device pointers (16-byte aligned) and is ordered on `stream`; the host
+ * form stages through temporary device buffers. */
+int sr_engine_normalize_features(sr_engine *e, const float *raw11, const int32_t *genre_id, int64_t n, int32_t n_genres,
+                                 float *out, float *minmax);
+int sr_engine_normalize_features_dev(sr_engine *e, const float *d_raw11, const int32_t *d_genre_id, int64_t n,
+                                     int32_t n_genres, float *d_out, float *d_minmax, void *stream);
+
+/* SURVEY 8 f4 -- genre name -> genre id for `n` songs (host only, no engine needed).
+ * mode 0: order of first appearance = what DataManager.cpp:244-250 yields with one OpenMP thread
+ * (with more threads the reference's ids depend on scheduling); mode 1: rank of the name in
+ * sorted (byte-wise) order -- deterministic whatever the order of the rows. */
+int sr_genre_ids(const char *const *names, int64_t n, int mode, int32_t *ids, int32_t *n_genres);
 
 /* Blocks until everything enqueued on the engine's own stream has finished. */
 int sr_engine_synchronize(sr_engine *e);

@@ -332,6 +332,51 @@ void sr_oracle_merge_parts(const int32_t *in_idx, const float *in_score,
     }
 }
 
+/* ---- the min-max normalisation step of preprocessing ----------------------
+ * Restates DataManager.cpp:270-301.  raw: n x 11 (danceability .. tempo, the order of
+ * DataManager.cpp:156-159), genre_id: n, out: n x 12.
+ *   - min/max per column with std::min / std::max semantics: the running value is kept
+ *     unless the new one is strictly smaller / larger, so NaN entries never enter (:273-281);
+ *     starting values numeric_limits<float>::max() / lowest() (:270-271);
+ *   - range = max - min; range > 0.0001f ? (x - min) / range : 0.5f            (:291-296)
+ *   - out[11] = (float)genre_id / max(1, n_genres - 1)                          (:299)
+ * One deliberate normalisation of an order artefact: a column minimum / maximum of zero is
+ * taken as +0.0f whatever the signs and order of the zeros in the column (the reference keeps
+ * whichever zero it met first).  minmax_out (22 floats: 11 minima, 11 maxima) may be NULL. */
+void sr_oracle_minmax_normalize(const float *raw, const int32_t *genre_id, int64_t n, int32_t n_genres,
+                                float *out, float *minmax_out)
+{
+    float mn[SR_FEATURES - 1], mx[SR_FEATURES - 1];
+    for (int j = 0; j < SR_FEATURES - 1; ++j) {
+        mn[j] = 3.402823466e+38f;
+        mx[j] = -3.402823466e+38f;
+    }
+    for (int64_t i = 0; i < n; ++i)
+        for (int j = 0; j < SR_FEATURES - 1; ++j) {
+            const float v = raw[i * (SR_FEATURES - 1) + j];
+            if (v < mn[j]) mn[j] = v;
+            if (v > mx[j]) mx[j] = v;
+        }
+    for (int j = 0; j < SR_FEATURES - 1; ++j) {
+        if (mn[j] == 0.0f) mn[j] = 0.0f;
+        if (mx[j] == 0.0f) mx[j] = 0.0f;
+    }
+    const int gden_i = n_genres - 1 > 1 ? n_genres - 1 : 1;
+    const float gden = (float)gden_i;
+    for (int64_t i = 0; i < n; ++i) {
+        for (int j = 0; j < SR_FEATURES - 1; ++j) {
+            const float range = mx[j] - mn[j];
+            out[i * SR_FEATURES + j] = range > 0.0001f ? (raw[i * (SR_FEATURES - 1) + j] - mn[j]) / range : 0.5f;
+        }
+        out[i * SR_FEATURES + SR_FEATURES - 1] = (float)genre_id[i] / gden;
+    }
+    if (minmax_out)
+        for (int j = 0; j < SR_FEATURES - 1; ++j) {
+            minmax_out[j] = mn[j];
+            minmax_out[SR_FEATURES - 1 + j] = mx[j];
+        }
+}
+
 int sr_oracle_max_threads(void)
 {
 #ifdef _OPENMP

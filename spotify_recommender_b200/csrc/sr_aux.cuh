@@ -255,6 +255,116 @@ __global__ void gather_rows_kernel(const float *raw, int64_t n, int32_t id_base,
     o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
 }
 
+// ---- min-max normalisation of the preprocessing step (DataManager.cpp:270-301)
+// raw: n x 11 row-major (danceability .. tempo), flat-indexed so every load is coalesced.  The grid is a
+// multiple of 11 blocks, so the flat stride is a multiple of 11 and a thread only ever meets ONE column:
+// one running minimum and maximum per thread, folded through shared and then global atomics on the
+// orderable encoding (min/max are order-independent: the result is deterministic).  NaN never enters
+// (std::min / std::max keep the running value unless the new one compares smaller / larger, :278-279).
+constexpr int kRawF = kF - 1;
+constexpr int kNormRows = 256;  // rows per block iteration of normalize_kernel (one per thread)
+// mm[0..10]: ~ord(min), mm[11..21]: ord(max) -- both grow under atomicMax, so a zeroed buffer is "empty"
+__global__ void __launch_bounds__(256) minmax_kernel(const float *raw, int64_t n, uint32_t *mm)
+{
+    __shared__ uint32_t s_mm[2 * kRawF];
+    if (threadIdx.x < 2 * kRawF) s_mm[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t total = n * kRawF;
+    const int64_t total4 = total / 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // multiple of 11 (in 128-bit loads, too)
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // element 4*e4 + k of a 128-bit load sits in column (4*first + k) mod 11 on every iteration
+    int col[4];
+    float mn[4], mx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        col[k] = (int)((4 * first + k) % kRawF);
+        mn[k] = 3.402823466e+38f;
+        mx[k] = -3.402823466e+38f;
+    }
+    bool any = false;
+    const float4 *raw4 = reinterpret_cast<const float4 *>(raw);
+    for (int64_t e4 = first; e4 < total4; e4 += stride) {
+        const float4 v = __ldg(raw4 + e4);
+        const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (x[k] < mn[k]) mn[k] = x[k];
+            if (x[k] > mx[k]) mx[k] = x[k];
+        }
+        any = true;
+    }
+    if (any) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            atomicMax(&s_mm[col[k]], ~f2ord(mn[k]));
+            atomicMax(&s_mm[kRawF + col[k]], f2ord(mx[k]));
+        }
+    }
+    // the (at most three) elements after the last whole 128-bit load
+    if (first < total - total4 * 4) {
+        const int64_t e = total4 * 4 + first;
+        const float v = raw[e];
+        const int c = (int)(e % kRawF);
+        float a = 3.402823466e+38f, b = -3.402823466e+38f;
+        if (v < a) a = v;
+        if (v > b) b = v;
+        atomicMax(&s_mm[c], ~f2ord(a));
+        atomicMax(&s_mm[kRawF + c], f2ord(b));
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kRawF && s_mm[threadIdx.x]) atomicMax(&mm[threadIdx.x], s_mm[threadIdx.x]);
+}
+
+// out: n x 12.  (x - min) / range in IEEE arithmetic when range > 1e-4f, else 0.5f (:291-296); the last
+// column is genre_id / max(1, n_genres - 1) (:299).  A zero minimum / maximum counts as +0.
+// 256 rows per block iteration: the 44-byte rows are staged through shared memory with 128-bit loads
+// (256 x 44 B is a multiple of 16), read back one row per thread (stride 11 words: conflict-free) and
+// written as three 128-bit stores per row.
+__global__ void __launch_bounds__(kNormRows) normalize_kernel(const float *raw, const int32_t *genre, int64_t n, float genre_den,
+                                                              const uint32_t *mm, float *out, float *minmax_out)
+{
+    __shared__ float s_mn[kRawF], s_rg[kRawF];
+    __shared__ __align__(16) float s_rows[kNormRows * kRawF];
+    if (threadIdx.x < kRawF) {
+        float mn = ord2f(~mm[threadIdx.x]), mx = ord2f(mm[kRawF + threadIdx.x]);
+        if (mn == 0.0f) mn = 0.0f;
+        if (mx == 0.0f) mx = 0.0f;
+        s_mn[threadIdx.x] = mn;
+        s_rg[threadIdx.x] = __fsub_rn(mx, mn);
+        if (minmax_out && blockIdx.x == 0) {
+            minmax_out[threadIdx.x] = mn;
+            minmax_out[kRawF + threadIdx.x] = mx;
+        }
+    }
+    const int64_t chunks = (n + kNormRows - 1) / kNormRows;
+    for (int64_t ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const int64_t row0 = ch * kNormRows;
+        const int rows = (int)min((int64_t)kNormRows, n - row0);
+        __syncthreads();  // s_rows is free (and, first time round, s_mn / s_rg are written)
+        const float *src = raw + row0 * kRawF;
+        if (rows == kNormRows) {
+            const float4 *src4 = reinterpret_cast<const float4 *>(src);
+            float4 *dst4 = reinterpret_cast<float4 *>(s_rows);
+            for (int i = threadIdx.x; i < kNormRows * kRawF / 4; i += kNormRows) dst4[i] = __ldg(src4 + i);
+        } else {
+            for (int i = threadIdx.x; i < rows * kRawF; i += kNormRows) s_rows[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < rows) {
+            float v[kF];
+#pragma unroll
+            for (int j = 0; j < kRawF; ++j)
+                v[j] = s_rg[j] > 0.0001f ? __fdiv_rn(__fsub_rn(s_rows[threadIdx.x * kRawF + j], s_mn[j]), s_rg[j]) : 0.5f;
+            v[kF - 1] = __fdiv_rn((float)genre[row0 + threadIdx.x], genre_den);
+            float4 *o = reinterpret_cast<float4 *>(out) + (row0 + threadIdx.x) * 3;
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            o[2] = make_float4(v[8], v[9], v[10], v[11]);
+        }
+    }
+}
+
 // ---- self-test hook: the engine's division, element-wise (tests only) ----------------
 __global__ void div_selftest_kernel(const float *a, const float *b, float *out, int n)
 {

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -115,10 +116,11 @@ struct sr_engine {
     int settle_at = 0;  // 0: cap / 16
     int trigger_at = 0; // 0: cap / 2
     int hit_cap = 0;   // hit-buffer entries per query in shared memory (0: sized from K)
+    int bound_tiles = 0;    // layout tiles (of S x 256 songs) the bound pass samples (0: 48 for k <= 16, else 128)
     bool profile = false;
 
     // batch workspace (grow-only)
-    DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, tile_ctr, pool_cnt, pool, out_idx, out_score, qin, exin;
+    DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, tile_ctr, pool_cnt, pool, out_idx, out_score, qin, exin, minmax;
     unsigned long long *d_stats = nullptr;  // [16]
     unsigned long long *d_irregular = nullptr;
     int32_t *d_flag = nullptr;
@@ -349,8 +351,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     // enough full tiles, else the exact sample
     const int64_t full_tiles = e->n / TS;
     const int nblk = K + 1;                                  // disjoint blocks of sample songs
-    // sample tiles: 128 layout tiles on large stores, never more than ~6 % of the store
-    const int n_sample = (int)std::min<int64_t>({(int64_t)128 / (v.threads / kLT), std::max<int64_t>(4, full_tiles / 16), full_tiles / 4});
+    // sample tiles: 48 (short lists) or 128 layout tiles on large stores, never more than ~6 % of the store
+    const int n_sample = (int)std::min<int64_t>({(int64_t)(e->bound_tiles > 0 ? e->bound_tiles : (K <= 16 ? 48 : 128)) / (v.threads / kLT), std::max<int64_t>(4, full_tiles / 16), full_tiles / 4});
     const bool use_bound = e->bound && nblk <= kLT / 2 && n_sample >= 4 && (int64_t)n_sample * TS >= 64 * (int64_t)nblk;
 
     int rc;
@@ -585,7 +587,7 @@ void sr_engine_destroy(sr_engine *e)
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto &t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->tile_ctr, &e->pool_cnt, &e->pool,
+    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->tile_ctr, &e->pool_cnt, &e->pool, &e->minmax,
                       &e->out_idx, &e->out_score, &e->qin, &e->exin};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -696,6 +698,80 @@ int sr_engine_gather_rows_dev(sr_engine *e, const int32_t *d_ids, int count, flo
     return SR_OK;
 }
 
+// genre name -> id.  The reference hands out ids first-come inside an OpenMP
+// critical section (DataManager.cpp:244-250), so they depend on thread scheduling; mode 0
+// restates what it does with ONE thread (order of first appearance), mode 1 is the
+// deterministic replacement (rank of the name in sorted order).  Host only.
+int sr_genre_ids(const char *const *names, int64_t n, int mode, int32_t *ids, int32_t *n_genres)
+{
+    if (!names || !ids || n < 0 || (mode != 0 && mode != 1)) return SR_EINVAL;
+    std::map<std::string, int32_t> seen;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!names[i]) return SR_EINVAL;
+        auto it = seen.find(names[i]);
+        if (it == seen.end()) it = seen.emplace(names[i], (int32_t)seen.size()).first;
+        ids[i] = it->second;
+    }
+    if (mode == 1) {
+        std::vector<int32_t> rank(seen.size());
+        int32_t r = 0;
+        for (const auto &kv : seen) rank[kv.second] = r++;  // std::map iterates in sorted key order
+        for (int64_t i = 0; i < n; ++i) ids[i] = rank[ids[i]];
+    }
+    if (n_genres) *n_genres = (int32_t)seen.size();
+    return SR_OK;
+}
+
+// the normalisation step of the reference's preprocessing (DataManager.cpp:270-301) on the GPU
+int sr_engine_normalize_features_dev(sr_engine *e, const float *d_raw11, const int32_t *d_genre, int64_t n, int32_t n_genres,
+                                     float *d_out, float *d_minmax, void *stream)
+{
+    if (!e) return SR_EINVAL;
+    if (!d_raw11 || !d_genre || !d_out) return fail(e, SR_EINVAL, "normalize_features: null pointer");
+    if (n <= 0 || n > 0x7fffffffLL) return fail(e, SR_EINVAL, "normalize_features: n must be in [1, 2^31) (got %lld)", (long long)n);
+    if (n_genres < 1) return fail(e, SR_EINVAL, "normalize_features: n_genres must be positive (got %d)", n_genres);
+    SR_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = pick_stream(e, stream);
+    int rc;
+    if ((rc = ensure(e, e->minmax, 2 * kRawF * 4))) return rc;
+    SR_CUDA(cudaMemsetAsync(e->minmax.p, 0, 2 * kRawF * 4, st));  // "empty" in the kernels' encoding
+    const int64_t want = (n * kRawF / 4 + 256 * 4 - 1) / (256 * 4);  // ~4 128-bit loads per thread
+    const int blocks = (int)std::max<int64_t>(kRawF, std::min<int64_t>((int64_t)e->sm_count * 8 / kRawF * kRawF, (want + kRawF - 1) / kRawF * kRawF));
+    minmax_kernel<<<blocks, 256, 0, st>>>(d_raw11, n, (uint32_t *)e->minmax.p);
+    SR_CUDA(cudaGetLastError());
+    const float genre_den = (float)std::max(1, n_genres - 1);
+    const int nblocks = (int)std::min<int64_t>((int64_t)e->sm_count * 8, (n + kNormRows - 1) / kNormRows);
+    normalize_kernel<<<nblocks, kNormRows, 0, st>>>(d_raw11, d_genre, n, genre_den, (const uint32_t *)e->minmax.p, d_out, d_minmax);
+    SR_CUDA(cudaGetLastError());
+    e->launches += 2;
+    return SR_OK;
+}
+
+int sr_engine_normalize_features(sr_engine *e, const float *raw11, const int32_t *genre_id, int64_t n, int32_t n_genres,
+                                 float *out, float *minmax_out)
+{
+    if (!e) return SR_EINVAL;
+    if (!raw11 || !genre_id || !out) return fail(e, SR_EINVAL, "normalize_features: null pointer");
+    if (n <= 0 || n > 0x7fffffffLL) return fail(e, SR_EINVAL, "normalize_features: n must be in [1, 2^31) (got %lld)", (long long)n);
+    SR_CUDA(cudaSetDevice(e->device));
+    float *d_raw = nullptr, *d_out = nullptr, *d_mm = nullptr;
+    int32_t *d_genre = nullptr;
+    cudaError_t err;
+    int rc = SR_OK;
+    if ((err = cudaMalloc(&d_raw, (size_t)n * kRawF * 4)) != cudaSuccess || (err = cudaMalloc(&d_out, (size_t)n * kF * 4)) != cudaSuccess ||
+        (err = cudaMalloc(&d_genre, (size_t)n * 4)) != cudaSuccess || (err = cudaMalloc(&d_mm, 2 * kRawF * 4)) != cudaSuccess ||
+        (err = cudaMemcpyAsync(d_raw, raw11, (size_t)n * kRawF * 4, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess ||
+        (err = cudaMemcpyAsync(d_genre, genre_id, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess)
+        rc = fail(e, SR_ECUDA, "normalize_features: %s", cudaGetErrorString(err));
+    if (!rc) rc = sr_engine_normalize_features_dev(e, d_raw, d_genre, n, n_genres, d_out, d_mm, SR_ENGINE_OWN_STREAM);
+    if (!rc && ((err = cudaMemcpyAsync(out, d_out, (size_t)n * kF * 4, cudaMemcpyDeviceToHost, e->stream)) != cudaSuccess ||
+                (minmax_out && (err = cudaMemcpyAsync(minmax_out, d_mm, 2 * kRawF * 4, cudaMemcpyDeviceToHost, e->stream)) != cudaSuccess) ||
+                (err = cudaStreamSynchronize(e->stream)) != cudaSuccess))
+        rc = fail(e, SR_ECUDA, "normalize_features: %s", cudaGetErrorString(err));
+    cudaFree(d_raw); cudaFree(d_out); cudaFree(d_genre); cudaFree(d_mm);
+    return rc;
+}
+
 int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k, int32_t *out_idx, float *out_score)
 {
     if (!e) return SR_EINVAL;
@@ -760,6 +836,9 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
         e->trigger_at = (int)value;
     } else if (!strcmp(key, "bound")) {
         e->bound = value != 0;
+    } else if (!strcmp(key, "bound_tiles")) {
+        if (value != 0 && (value < 8 || value > 1024)) return fail(e, SR_EINVAL, "bound_tiles must be 0 (auto) or in [8, 1024]");
+        e->bound_tiles = (int)value;
     } else if (!strcmp(key, "hit_cap")) {
         if (value != 0 && (value < 32 || value > 1024 || value % 32)) return fail(e, SR_EINVAL, "hit_cap must be 0 (auto) or a multiple of 32 in [32, 1024]");
         e->hit_cap = (int)value;

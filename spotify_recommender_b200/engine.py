@@ -24,7 +24,7 @@ EXPORTS = [
     "sr_engine_query_by_vector", "sr_engine_query_by_index_dev", "sr_engine_query_by_vector_dev",
     "sr_engine_merge_topk_dev", "sr_engine_gather_rows_dev", "sr_engine_all_pairs_topk", "sr_engine_set_option", "sr_engine_get_stat",
     "sr_engine_get_timing", "sr_engine_variant_name", "sr_engine_measure_fp32", "sr_engine_selftest_div",
-    "sr_engine_synchronize",
+    "sr_engine_synchronize", "sr_engine_normalize_features", "sr_engine_normalize_features_dev", "sr_genre_ids",
 ]
 
 
@@ -72,8 +72,23 @@ def load_library() -> C.CDLL:
     L.sr_engine_measure_fp32.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.sr_engine_selftest_div.argtypes = [vp, vp, vp, i32, vp]
     L.sr_engine_synchronize.argtypes = [vp]
+    L.sr_engine_normalize_features.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    L.sr_engine_normalize_features_dev.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
+    L.sr_genre_ids.argtypes = [C.POINTER(C.c_char_p), i64, i32, vp, C.POINTER(C.c_int32)]
     _lib = L
     return L
+
+
+def genre_ids(names: list[str], sorted_ids: bool = True) -> tuple[np.ndarray, int]:
+    """Genre name -> id (sr_genre_ids): first-appearance order (the reference with one thread) or sorted."""
+    L = load_library()
+    arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+    ids = np.empty(len(names), np.int32)
+    ng = C.c_int32(0)
+    rc = L.sr_genre_ids(arr, len(names), 1 if sorted_ids else 0, ids.ctypes.data_as(C.c_void_p), C.byref(ng))
+    if rc:
+        raise EngineError(rc, "sr_genre_ids: bad arguments")
+    return ids, int(ng.value)
 
 
 def variant_names() -> list[str]:
@@ -178,6 +193,23 @@ class Engine:
         out_s = np.empty((q_hi - q_lo, k), np.float32) if scores else None
         self._check(self.L.sr_engine_all_pairs_topk(self.h, q_lo, q_hi, k, _ptr(out_i), _ptr(out_s)))
         return out_i, out_s
+
+    # -- preprocessing: min-max normalisation (DataManager.cpp:270-301) --------
+    def normalize_features(self, raw11: np.ndarray, genre_id: np.ndarray, n_genres: int):
+        """raw11 (n x 11 float32), genre ids -> (n x 12 normalised features, 22 minima/maxima); host buffers."""
+        raw11 = np.ascontiguousarray(raw11, np.float32)
+        genre_id = np.ascontiguousarray(genre_id, np.int32)
+        n = raw11.shape[0]
+        assert raw11.shape == (n, 11) and genre_id.shape == (n,)
+        out = np.empty((n, 12), np.float32)
+        mm = np.empty(22, np.float32)
+        self._check(self.L.sr_engine_normalize_features(self.h, _ptr(raw11), _ptr(genre_id), n, n_genres, _ptr(out), _ptr(mm)))
+        return out, mm
+
+    def normalize_features_dev(self, d_raw11, d_genre_id, n: int, n_genres: int, d_out, d_minmax=None,
+                               stream: int | None = None) -> None:
+        self._check(self.L.sr_engine_normalize_features_dev(self.h, _ptr(d_raw11), _ptr(d_genre_id), n, n_genres,
+                                                            _ptr(d_out), _ptr(d_minmax), _stream(stream)))
 
     # -- queries, DEVICE buffers (stream-ordered, not synchronised) ------------
     def query_by_index_dev(self, d_qidx, nq: int, k: int, d_out_idx, d_out_score=None, stream: int | None = None) -> None:

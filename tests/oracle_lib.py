@@ -40,6 +40,7 @@ class Oracle:
                                            C.c_int32, _i32p, _f32p, C.c_int]
         L.sr_oracle_query_index.argtypes = [_f32p, C.c_int64, _i32p, C.c_int, C.c_int, _i32p, _f32p, C.c_int]
         L.sr_oracle_merge_parts.argtypes = [_i32p, _f32p, C.c_int, C.c_int, C.c_int, _i32p, _f32p]
+        L.sr_oracle_minmax_normalize.argtypes = [_f32p, _i32p, C.c_int64, C.c_int32, _f32p, _f32p]
         L.sr_oracle_max_threads.restype = C.c_int
         self.L = L
 
@@ -89,6 +90,16 @@ class Oracle:
             ex_p = ex.ctypes.data_as(C.c_void_p)
         self.L.sr_oracle_query_rows(feats, feats.shape[0], q, ex_p, q.shape[0], k, id_base, oi, os_, threads)
         return oi, os_
+
+    def minmax_normalize(self, raw11, genre_id, n_genres: int):
+        """DataManager.cpp:270-301 restated: (n x 12 features, 22 minima/maxima)."""
+        raw11 = np.ascontiguousarray(raw11, np.float32)
+        genre_id = np.ascontiguousarray(genre_id, np.int32)
+        n = raw11.shape[0]
+        out = np.empty((n, 12), np.float32)
+        mm = np.empty(22, np.float32)
+        self.L.sr_oracle_minmax_normalize(raw11, genre_id, n, n_genres, out, mm)
+        return out, mm
 
     def merge_parts(self, idx, score):
         idx = np.ascontiguousarray(idx, np.int32)

@@ -143,7 +143,7 @@ def test_native_libraries_export_every_declared_symbol():
     import recommender_lib
     build.build_all()
     hdr = open(os.path.join(build.ROOT, "include", "sr_engine.h")).read()
-    declared = sorted(set(re.findall(r"\b(sr_engine_[a-z0-9_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(sr_(?:engine_)?[a-z0-9_]+)\s*\(", hdr)))
     assert set(declared) == set(engine.EXPORTS)
     lib = engine.load_library()
     for name in declared:
