@@ -277,9 +277,10 @@ def run_ours(args) -> None:
             traffic = json.load(fh).get("dram_bytes_per_launch")
     except Exception:
         pass
+    kernel_shape = variant_names()[eng.stat("variant")]  # of the timed batches (the HBM sweep below uses another)
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-        "traffic": traffic, "kernel": "scan_kernel<%s>" % variant_names()[eng.stat("variant")],
+        "traffic": traffic, "kernel": "scan_kernel<%s>" % kernel_shape,
         "launches_timed": scan_n, "avg_launch_ms": scan_avg_ms,
         "peak_is": f"{sm_count} SMs x 128 FFMA lanes x 2 flop x {sm_max_mhz:.0f} MHz (nominal FP32, no tensor cores; "
                    "north_star: min(HBM, FP32) roofline; this batch is FP32-bound, Q* = 23)",
@@ -334,7 +335,7 @@ def run_ours(args) -> None:
                        "songs_total": n_total, "songs_per_gpu": hi - lo, "queries_per_batch": BATCH,
                        "top_k": TOPK, "parallelism": f"row-shard x{world}" + (" + NCCL all-gather + merge" if world > 1 else ""),
                        "l2": "store (2 x 480 MB per GPU) is larger than the 126 MB L2; every step uses a fresh query batch",
-                       "kernel_shape": variant_names()[eng.stat("variant")]},
+                       "kernel_shape": kernel_shape},
             "queries_per_s_at_10M": value / 1e7,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "song-pairs/s", "h2d_bytes_per_step": BATCH * 4,
