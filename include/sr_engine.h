@@ -119,6 +119,8 @@ int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k,
  *   "batch"     max queries per internal pass (workspace is sized for it)
  *   "sample"    threshold-bootstrap sample size per query (0 = off, else power of two <= 4096)
  *   "hit_cap"   hit-buffer entries per query per CTA (multiple of 32; 0 = sized from k)
+ *   "list_ws"   1 (default): the CTAs' top-k lists may live in an L2-resident workspace instead of shared
+ *               memory when that keeps the query tile at 256 queries (used for 16 < k <= 72); 0: never
  *   "bound_tiles" layout tiles (2048 songs each) sampled by the threshold bound pass (0 = auto: 48 for k <= 16, else 128)
  *   "trigger_at" a settle phase starts when some hit buffer holds this many ids (0 = cap / 2)
  *   "settle_at" ... and scores and merges every buffer holding at least this many (0 = cap / 16)

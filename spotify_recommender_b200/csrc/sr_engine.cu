@@ -116,11 +116,12 @@ struct sr_engine {
     int settle_at = 0;  // 0: cap / 16
     int trigger_at = 0; // 0: cap / 2
     int hit_cap = 0;   // hit-buffer entries per query in shared memory (0: sized from K)
+    int list_ws_opt = 1;    // allow the CTAs' lists in an L2-resident workspace when that keeps the query tile at full size
     int bound_tiles = 0;    // layout tiles (of S x 256 songs) the bound pass samples (0: 48 for k <= 16, else 128)
     bool profile = false;
 
     // batch workspace (grow-only)
-    DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, tile_ctr, pool_cnt, pool, out_idx, out_score, qin, exin, minmax;
+    DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, tile_ctr, pool_cnt, pool, out_idx, out_score, qin, exin, minmax, list_ws;
     unsigned long long *d_stats = nullptr;  // [16]
     unsigned long long *d_irregular = nullptr;
     int32_t *d_flag = nullptr;
@@ -295,6 +296,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     int vi = e->variant >= 0 ? e->variant : (nq <= 40 ? kAutoSmall : kAutoLarge);
     const Variant *vp = nullptr;
     int TS = 0, n_tiles = 0, groups = 0, gsize = 0, qt_cap = 0, cap = 0;
+    bool lists_in_smem = true;
     size_t stage_bytes = 0;
     for (int attempt = 0; attempt < 2 && !qt_cap; ++attempt) {
         if (attempt == 1) {  // the staged small-batch shape has little shared memory left for long lists
@@ -318,9 +320,18 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         for (int qtry = qt_max; qtry >= 1 && !qt_cap; qtry = (qtry > 8 ? qtry / 2 : qtry - 1)) {
             const int caps[4] = {e->hit_cap > 0 ? e->hit_cap : std::max(128, 4 * kk), std::max(128, 2 * kk),
                                  std::max(128, 3 * kk / 2), qtry <= 64 ? std::max(32, kk) : 0};
-            for (int ci = 0; ci < 4 && !qt_cap; ++ci) {
-                const int ctry = std::min(1024, (caps[ci] + 31) / 32 * 32);
-                if (ctry > 0 && scan_smem_bytes(qtry, ctry, K, stage_bytes) <= smem_budget) { qt_cap = qtry; cap = ctry; }
+            // lists in shared memory first; for a full-size query tile of a one-CTA shape also with the
+            // lists in an L2-resident workspace (a settle then costs two global round trips, a query
+            // tile of half the size costs 6 % of the whole scan; measured: wins up to k ~ 72, beyond
+            // that twice as many CTAs per query with long lists of their own cost more)
+            for (int in_smem = 1; in_smem >= 0 && !qt_cap; --in_smem) {
+                if (!in_smem && !(e->list_ws_opt && K <= 72 && qtry == qt_max && qtry >= 128 && vp->ctas == 1 && !vp->staged)) break;
+                for (int ci = 0; ci < 4 && !qt_cap; ++ci) {
+                    const int ctry = std::min(1024, (caps[ci] + 31) / 32 * 32);
+                    if (ctry > 0 && scan_smem_bytes(qtry, ctry, K, stage_bytes, in_smem != 0) <= smem_budget) {
+                        qt_cap = qtry; cap = ctry; lists_in_smem = in_smem != 0;
+                    }
+                }
             }
         }
     }
@@ -330,7 +341,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     const int nqt0 = (gsize + qt_cap - 1) / qt_cap;
     const int qt = (gsize + nqt0 - 1) / nqt0;
     const int nqt = (gsize + qt - 1) / qt;
-    const size_t smem = scan_smem_bytes(qt, cap, K, stage_bytes);
+    if (!lists_in_smem && scan_smem_bytes(qt, cap, K, stage_bytes, true) <= (size_t)216 * 1024 / v.ctas) lists_in_smem = true;  // few queries: they fit after all
+    const size_t smem = scan_smem_bytes(qt, cap, K, stage_bytes, lists_in_smem);
     int ctas = 0;
     SR_CUDA(v.occ(&ctas, smem));
     if (ctas < 1) return fail(e, SR_ECUDA, "scan kernel %s does not fit one SM (smem %zu)", v.name, smem);
@@ -367,6 +379,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->tile_ctr, (size_t)(nqt + 1) * 8))) return rc;
     if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
     if ((rc = ensure(e, e->pool, (size_t)nq * segs * K * 8))) return rc;
+    if (!lists_in_smem && (rc = ensure(e, e->list_ws, (size_t)grid * qt * K * 8))) return rc;
 
     SR_CUDA(cudaMemsetAsync(e->gslot.p, 0, (size_t)nq * nslot * 4, st));
     if (use_bound) SR_CUDA(cudaMemsetAsync(e->gbound.p, 0, (size_t)nq * nblk * 4, st));
@@ -414,6 +427,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.pool = (uint64_t *)e->pool.p + (size_t)g0 * segs * K; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
         a.segs = segs;
         a.g_best = (uint32_t *)e->gbest.p + g0;
+        a.list_ws = lists_in_smem ? nullptr : (uint64_t *)e->list_ws.p;
         a.stats = e->d_stats;
         const int gnqt = (gq + qt - 1) / qt;
         std::lock_guard<std::mutex> lock(g_bank_mutex);
@@ -587,7 +601,7 @@ void sr_engine_destroy(sr_engine *e)
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto &t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->tile_ctr, &e->pool_cnt, &e->pool, &e->minmax,
+    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->tile_ctr, &e->pool_cnt, &e->pool, &e->minmax, &e->list_ws,
                       &e->out_idx, &e->out_score, &e->qin, &e->exin};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -836,6 +850,8 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
         e->trigger_at = (int)value;
     } else if (!strcmp(key, "bound")) {
         e->bound = value != 0;
+    } else if (!strcmp(key, "list_ws")) {
+        e->list_ws_opt = value != 0;
     } else if (!strcmp(key, "bound_tiles")) {
         if (value != 0 && (value < 8 || value > 1024)) return fail(e, SR_EINVAL, "bound_tiles must be 0 (auto) or in [8, 1024]");
         e->bound_tiles = (int)value;

@@ -59,6 +59,8 @@ struct ScanArgs {
     int upc, extra;          // work units per CTA: CTA b owns upc + (b < extra) units, in order
     int cpq;                 // DYN shapes: CTAs per query tile (the first grid - cpq*nqt tiles get one more)
     int *tile_ctr;           // DYN shapes: [nqt] next unclaimed song tile of each query tile
+    uint64_t *list_ws;       // non-null: the CTAs' top-K lists live here ([grid][qt][K], L2-resident) instead of in shared
+                             // memory -- long lists would otherwise halve the query tile
     int *visit_ctr;          // DYN shapes: [nqt] CTAs that joined a query tile after finishing their own
     int steal_max;           // DYN shapes: how many such late joiners a query tile admits (sizes the pool slab)
     const float *qraw;       // [nq][12] raw query rows            (all per-query arrays are
@@ -84,9 +86,9 @@ struct ScanArgs {
 };
 
 // `stage_bytes`: size of the TMA staging buffer for one song tile (0 for unstaged shapes)
-__host__ __device__ inline size_t scan_smem_bytes(int qt, int cap, int K, size_t stage_bytes = 0)
+__host__ __device__ inline size_t scan_smem_bytes(int qt, int cap, int K, size_t stage_bytes = 0, bool lists_in_smem = true)
 {
-    return (stage_bytes ? stage_bytes + 16 : 0) + (size_t)qt * K * 8 + (size_t)qt * (kF + 9 + cap) * 4 + 48;
+    return (stage_bytes ? stage_bytes + 16 : 0) + (lists_in_smem ? (size_t)qt * K * 8 : 0) + (size_t)qt * (kF + 9 + cap) * 4 + 48;
 }
 
 // ---- TMA (bulk async copy) staging of song tiles: global -> shared, completion on an mbarrier
@@ -453,7 +455,8 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + kTileBytes);          // STAGE only
     QueryCtx c;
     c.list = reinterpret_cast<uint64_t *>(smem_raw + (STAGE ? kTileBytes + 16 : 0));
-    c.qraw = reinterpret_cast<float *>(c.list + (size_t)a.qt * a.K);
+    c.qraw = reinterpret_cast<float *>(c.list + (a.list_ws ? 0 : (size_t)a.qt * a.K));
+    if (a.list_ws) c.list = a.list_ws + (size_t)blockIdx.x * a.qt * a.K;
     c.nthr = c.qraw + a.qt * kF;
     c.qn = c.nthr + a.qt;
     c.best = reinterpret_cast<uint32_t *>(c.qn + a.qt);

@@ -76,7 +76,7 @@ def test_golden_vectors(eng, oracle, case):
 
 
 @pytest.mark.parametrize("variant", range(6))
-def test_every_kernel_shape(eng, oracle, variant):
+def test_every_kernel_shape(eng, oracle, variant):  # k = 1, 10, 100; 257 queries
     n = 150_000
     f = synth.features(n)
     eng.set_option("variant", variant)
@@ -90,7 +90,8 @@ def test_every_kernel_shape(eng, oracle, variant):
 
 
 @pytest.mark.parametrize("n,nq,k", [(1, 1, 1), (2, 2, 1), (5, 5, 4), (33, 33, 7), (1000, 64, 10), (4097, 130, 100),
-                                    (40_000, 1500, 10), (200_000, 300, 333), (100_000, 1, 1024)])
+                                    (40_000, 1500, 10), (200_000, 300, 333), (100_000, 1, 1024),
+                                    (300_000, 600, 50), (150_000, 1300, 64)])  # last two: lists in the L2 workspace
 def test_sizes_and_ragged_batches(eng, oracle, n, nq, k):
     f = synth.features(n)
     eng.load_features(f)
