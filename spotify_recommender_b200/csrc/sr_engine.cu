@@ -378,7 +378,13 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->gslot, (size_t)nq * nslot * 4))) return rc;
     if ((rc = ensure(e, e->tile_ctr, (size_t)(nqt + 1) * 8))) return rc;
     if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
-    if ((rc = ensure(e, e->pool, (size_t)nq * segs * K * 8))) return rc;
+    // pool slab of a query: K keys per segment, plus (dynamic shapes) the hits a segment can leave unsettled
+    const int settle_at_eff = e->settle_at > 0 ? std::min(e->settle_at, cap) : std::max(4, cap / 16);
+    const int trigger_at_eff = e->trigger_at > 0 ? std::min(std::max(e->trigger_at, settle_at_eff), cap) : std::max(settle_at_eff, cap / 2);
+    const int64_t slab64 = (int64_t)segs * (K + (v.dynamic ? trigger_at_eff : 0));
+    if (slab64 * 8 * nq > ((int64_t)8 << 30)) return fail(e, SR_EINVAL, "k = %d with %d queries per pass needs a %lld-byte pool: lower the \"batch\" option", K, nq, (long long)(slab64 * 8 * nq));
+    const int slab = (int)slab64;
+    if ((rc = ensure(e, e->pool, (size_t)nq * slab * 8))) return rc;
     if (!lists_in_smem && (rc = ensure(e, e->list_ws, (size_t)grid * qt * K * 8))) return rc;
 
     SR_CUDA(cudaMemsetAsync(e->gslot.p, 0, (size_t)nq * nslot * 4, st));
@@ -419,13 +425,13 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.n_tiles = n_tiles;
         a.qraw = (float *)e->qraw.p + (size_t)g0 * kF; a.qn = (float *)e->qn.p + g0;
         a.exclude = (int32_t *)e->excl.p + g0; a.nq = gq; a.qt = qt;
-        a.K = K; a.cap = cap; a.settle_at = e->settle_at > 0 ? std::min(e->settle_at, cap) : std::max(4, cap / 16);
+        a.K = K; a.cap = cap; a.settle_at = settle_at_eff;
         a.refresh_every = std::max(1, std::min(8, 64 / qt));
-        a.trigger_at = e->trigger_at > 0 ? std::min(std::max(e->trigger_at, a.settle_at), cap) : std::max(a.settle_at, cap / 2);
+        a.trigger_at = trigger_at_eff;
         a.gslot = (uint32_t *)e->gslot.p + (size_t)g0 * nslot;
         a.nslot = nslot;
-        a.pool = (uint64_t *)e->pool.p + (size_t)g0 * segs * K; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
-        a.segs = segs;
+        a.pool = (uint64_t *)e->pool.p + (size_t)g0 * slab; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
+        a.segs = segs; a.slab = slab;
         a.g_best = (uint32_t *)e->gbest.p + g0;
         a.list_ws = lists_in_smem ? nullptr : (uint64_t *)e->list_ws.p;
         a.stats = e->d_stats;
@@ -476,7 +482,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     {
         FinalArgs f;
         f.pool = (uint64_t *)e->pool.p; f.pool_cnt = (int32_t *)e->pool_cnt.p;
-        f.nq = nq; f.K = K; f.segs = segs; f.out_idx = d_out_idx; f.out_score = d_out_score;
+        f.nq = nq; f.K = K; f.slab = slab; f.out_idx = d_out_idx; f.out_score = d_out_score;
         Scope sc(e, st, kFinalize);
         finalize_kernel<256><<<nq, 256, 0, st>>>(f);
         SR_CUDA(cudaGetLastError());
@@ -879,8 +885,9 @@ int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value)
     if (!e || !key || !value) return SR_EINVAL;
     SR_CUDA(cudaSetDevice(e->device));
     static const char *const dev_keys[] = {"filter_hits", "settles", "rescans", "rescored", "refilters",
-                                           "hot_cycles", "settle_cycles", "cta_cycles", "wait_cycles"};  // last four: -DSR_SCAN_TIMING builds only
-    for (int i = 0; i < 9; ++i) {
+                                           "hot_cycles", "settle_cycles", "cta_cycles", "wait_cycles",
+                                           "final_settle_cycles", "flush_cycles", "join_cycles", "prologue_cycles"};  // from hot_cycles on: -DSR_SCAN_TIMING builds only
+    for (int i = 0; i < 13; ++i) {
         if (!strcmp(key, dev_keys[i])) {
             unsigned long long h[16];
             SR_CUDA(cudaStreamSynchronize(e->stream));

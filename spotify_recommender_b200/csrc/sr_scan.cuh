@@ -59,6 +59,7 @@ struct ScanArgs {
     int upc, extra;          // work units per CTA: CTA b owns upc + (b < extra) units, in order
     int cpq;                 // DYN shapes: CTAs per query tile (the first grid - cpq*nqt tiles get one more)
     int *tile_ctr;           // DYN shapes: [nqt] next unclaimed song tile of each query tile
+    int slab;                // keys per query in the pool (segs x K, plus room for a segment's unsettled hits in DYN shapes)
     uint64_t *list_ws;       // non-null: the CTAs' top-K lists live here ([grid][qt][K], L2-resident) instead of in shared
                              // memory -- long lists would otherwise halve the query tile
     int *visit_ctr;          // DYN shapes: [nqt] CTAs that joined a query tile after finishing their own
@@ -88,7 +89,7 @@ struct ScanArgs {
 // `stage_bytes`: size of the TMA staging buffer for one song tile (0 for unstaged shapes)
 __host__ __device__ inline size_t scan_smem_bytes(int qt, int cap, int K, size_t stage_bytes = 0, bool lists_in_smem = true)
 {
-    return (stage_bytes ? stage_bytes + 16 : 0) + (lists_in_smem ? (size_t)qt * K * 8 : 0) + (size_t)qt * (kF + 9 + cap) * 4 + 48;
+    return (stage_bytes ? stage_bytes + 16 : 0) + (lists_in_smem ? (size_t)qt * K * 8 : 0) + (size_t)qt * (kF + 10 + cap) * 4 + 48;
 }
 
 // ---- TMA (bulk async copy) staging of song tiles: global -> shared, completion on an mbarrier
@@ -143,6 +144,7 @@ struct QueryCtx {  // shared-memory views of one query tile
     float *nthr, *qraw, *qn;
     uint32_t *best;
     int *cnt, *lcnt, *excl, *qid;
+    int *dirty;      // [qt] a tile was re-filtered / re-scanned for this query in this segment: pending hits may repeat list entries
     uint32_t *hit;   // [qt][cap] global ids that passed the filter, not yet scored
 };
 
@@ -353,6 +355,7 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
     publish(kth);
     bool rescanned = false;
     if (overflow) {
+        if (lane == 0) c.dirty[ql] = 1;
         if (c.best[ql] > best_before) {
             if (lane == 0) redo[atomicAdd(redo_cnt, 1)] = ql;  // re-filter the tile against the raised threshold
         } else {
@@ -464,7 +467,8 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     c.lcnt = c.cnt + a.qt;
     c.excl = c.lcnt + a.qt;
     c.qid = c.excl + a.qt;
-    c.hit = reinterpret_cast<uint32_t *>(c.qid + a.qt);
+    c.dirty = c.qid + a.qt;
+    c.hit = reinterpret_cast<uint32_t *>(c.dirty + a.qt);
     // s_flag[tile % 3] != 0: some hit buffer filled up during that tile (set by the appending
     // thread).  Three slots make the protocol race-free with ONE barrier per tile: slot t%3 is
     // read right after tile t's barrier, cleared after tile t+1's barrier (every read is done),
@@ -479,9 +483,9 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     if (threadIdx.x < 4) s_flag[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_redo_cnt[threadIdx.x] = 0;
 #ifdef SR_SCAN_TIMING
-    __shared__ int s_time[4];  // hot loop, settle phases, barrier wait, scratch
+    __shared__ int s_time[8];  // hot loop, settle phases, barrier wait, scratch, final settle, flush, join, prologue
     __shared__ long long s_t0;
-    if (threadIdx.x < 4) s_time[threadIdx.x] = 0;
+    if (threadIdx.x < 8) s_time[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_t0 = clock64();
 #endif
     int tphase = 0;
@@ -523,12 +527,14 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         const int nql = min(a.qt, a.nq - q0);
 
         // ---- segment prologue: bring the query tile's state into shared memory
+        SR_TIME_BEGIN(7);
         for (int ql = tid; ql < nql; ql += THREADS) {
             const int qid = q0 + ql;
             c.qid[ql] = qid;
             c.excl[ql] = a.exclude[qid];
             c.cnt[ql] = 0;
             c.lcnt[ql] = 0;
+            c.dirty[ql] = 0;
             c.qn[ql] = a.qn[qid];
             const uint32_t b = __ldcg(a.g_best + qid);
             c.best[ql] = b;
@@ -537,6 +543,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         for (int i = tid; i < nql * kF; i += THREADS) c.qraw[i] = a.qraw[(size_t)q0 * kF + i];
         __syncthreads();
 
+        SR_TIME_END(7);
         int it = 0, slot = 0;
         // this thread's S songs of store tile `t` -> registers: S/2 interleaved pairs, six 128-bit
         // loads each, every load two ready FFMA2 operands
@@ -746,18 +753,60 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             }
             tile = next_tile;
         }
-        if (DYN) {  // the last tile is not known in advance: settle whatever is still pending now
-            bool need = false;
+        SR_TIME_BEGIN(4);
+        if (DYN) {
+            // The last tile is not known in advance, so hits are still pending now (fewer than trigger_at
+            // per query).  Settling them one query at a time is a chain of dependent global round trips
+            // per query (rows, slots, thresholds) that nothing overlaps at the end of a segment.  Instead
+            // every warp walks the pending hits of ALL its queries 32 at a time -- one round of
+            // independent row loads -- and appends the exact keys that can still matter straight to the
+            // pool; the list is bypassed (finalize sorts the pool anyway).  Queries whose tile was
+            // re-filtered in this segment may hold hits that repeat list entries: they take the
+            // duplicate-checking settle.
             const int ql_mine = warp + WARPS * lane;
-            if (ql_mine < nql) need = c.cnt[ql_mine] > 0;
-            uint32_t todo = __ballot_sync(0xffffffffu, need);
+            const bool mine = ql_mine < nql;
+            const bool slow = mine && c.dirty[ql_mine] && c.cnt[ql_mine] > 0;
+            uint32_t todo = __ballot_sync(0xffffffffu, slow);
             while (todo) {
                 const int l = __ffs(todo) - 1;
                 todo &= todo - 1;
                 warp_settle(a, c, warp + WARPS * l, 0, 0, s_redo, s_redo_cnt);  // cnt <= cap here: no overflow
             }
+            const int my_cnt = (mine && !c.dirty[ql_mine]) ? min(c.cnt[ql_mine], a.cap) : 0;
+            int offs = my_cnt;  // inclusive, then exclusive, prefix sum over the warp's queries
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, offs, d);
+                if (lane >= d) offs += o;
+            }
+            const int total = __shfl_sync(0xffffffffu, offs, 31);
+            offs -= my_cnt;
+            for (int base = 0; base < total; base += 32) {
+                const int idx = base + lane;
+                int L = 0;  // owner = the last lane whose range starts at or before idx
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int o = __shfl_sync(0xffffffffu, offs, L + step);
+                    if (o <= idx) L += step;
+                }
+                const int o_own = __shfl_sync(0xffffffffu, offs, L);
+                if (idx < total) {
+                    const int ql = warp + WARPS * L;
+                    float q[kF];
+#pragma unroll
+                    for (int j = 0; j < kF; ++j) q[j] = c.qraw[ql * kF + j];
+                    const uint64_t key = exact_key(a, (int64_t)c.hit[(size_t)ql * a.cap + (idx - o_own)] - a.id_base, q, c.qn[ql], c.excl[ql]);
+                    const uint64_t floor_key = (uint64_t)max(c.best[ql], __ldcg(a.g_best + c.qid[ql])) << 32;
+                    if (key != 0ull && key >= floor_key)
+                        a.pool[(size_t)(q0 + ql) * a.slab + atomicAdd(a.pool_cnt + q0 + ql, 1)] = key;
+                }
+            }
+            if (my_cnt) c.cnt[ql_mine] = 0;
+            if (a.stats && lane == 0 && total) atomicAdd(a.stats + 3, (unsigned long long)total);
             __syncthreads();
         }
+        SR_TIME_END(4);
+        SR_TIME_BEGIN(5);
         // ---- segment epilogue: hand this CTA's exact survivors to the per-query pool
         // (the last tile's settle phase and its closing barrier have just run)
         // (only keys that can still make the final top-K: score >= the best known bound)
@@ -765,7 +814,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             const int n = c.lcnt[ql];
             if (n == 0) continue;
             const uint64_t floor_key = (uint64_t)max(c.best[ql], __ldcg(a.g_best + c.qid[ql])) << 32;
-            uint64_t *slab = a.pool + (size_t)(q0 + ql) * a.segs * a.K;
+            uint64_t *slab = a.pool + (size_t)(q0 + ql) * a.slab;
             const uint64_t *list = c.list + (size_t)ql * a.K;
             for (int b0 = 0; b0 < n; b0 += 32) {
                 const int i = b0 + lane;
@@ -780,6 +829,8 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             }
         }
         __syncthreads();
+        SR_TIME_END(5);
+        SR_TIME_BEGIN(6);
         if (DYN) {
             // this query tile has no unclaimed song tiles left: join another one that has (CTAs
             // per query tile rarely divide the grid evenly, and settle work differs between tiles)
@@ -797,6 +848,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             }
             __syncthreads();
             const int cand = __reduce_max_sync(0xffffffffu, s_next[3]);
+            SR_TIME_END(6);
             if (cand < 0) break;
             qtile = cand;
         } else {
@@ -813,6 +865,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         atomicAdd(a.stats + 6, (unsigned long long)(unsigned)s_time[1]);
         atomicAdd(a.stats + 7, (unsigned long long)(clock64() - s_t0));
         atomicAdd(a.stats + 8, (unsigned long long)(unsigned)s_time[2]);
+        for (int i = 4; i < 8; ++i) atomicAdd(a.stats + 5 + i, (unsigned long long)(unsigned)s_time[i]);
     }
 #endif
 }

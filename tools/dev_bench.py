@@ -50,3 +50,4 @@ for k in ks:
             cta, hot, st, wt = e.stat("cta_cycles"), e.stat("hot_cycles"), e.stat("settle_cycles"), e.stat("wait_cycles")
             print("   in-kernel cycles (thread 0 of every CTA): hot loop %.1f%%  settle phases %.1f%%  tile barrier wait %.1f%%  other (prologue, flush, joins) %.1f%%; CTA-cycles/launch/SM %.0f" % (
                 100.0 * hot / cta, 100.0 * st / cta, 100.0 * wt / cta, 100.0 * (cta - hot - st - wt) / cta, cta / max(1, cnt) / 148), flush=True)
+            print("   of which: " + "  ".join("%s %.1f%%" % (k, 100.0 * e.stat(k + "_cycles") / cta) for k in ("prologue", "final_settle", "flush", "join")), flush=True)
