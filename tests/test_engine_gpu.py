@@ -237,15 +237,18 @@ def test_all_pairs_neighbour_table(eng, oracle):
     assert np.array_equal(back.view(np.uint32), gs[:200, 0].view(np.uint32))
 
 
-def test_clustered_store_takes_the_refilter_path(eng, oracle):
+@pytest.mark.parametrize("k,nq", [(10, 64), (50, 600), (100, 300)])
+def test_clustered_store_takes_the_refilter_path(eng, oracle, k, nq):
     """A genre-sorted store whose clusters the bound pass cannot see (bound off, tiny sample):
-    tiles overflow their hit buffers and are re-filtered against the raised threshold."""
-    n, k = 300_000, 10
+    tiles overflow their hit buffers and are re-filtered against the raised threshold.  (k = 50 keeps the
+    CTA lists in the L2 workspace; re-filtered queries end their segment through the duplicate-checking
+    settle, the others through the pending pass straight to the pool.)"""
+    n = 300_000
     rng = np.random.default_rng(9)
     centers = rng.random((30, 12), dtype=np.float32)
     f = (centers[np.arange(n) // (n // 30 + 1)] + 0.02 * rng.random((n, 12), dtype=np.float32)).astype(np.float32)
     eng.load_features(f)
-    q = synth.query_indices(64, n)
+    q = synth.query_indices(nq, n)
     try:
         eng.set_option("bound", 0); eng.set_option("sample", 0); eng.set_option("reset", 1)
         got = eng.query_by_index(q, k)
