@@ -32,7 +32,9 @@
 //     buffered hits raise the threshold and the CTA re-filters the tile against it; if the
 //     threshold did not move (mass ties, NaN queries) the owning warp scores the tile exactly.
 //   flush: after its last tile of a query tile the CTA appends the list entries that can
-//     still matter to the per-query pool; finalize_kernel merges the pool into the ordered top-K.
+//     still matter to the per-query pool -- and, in the DYN shapes, the exact keys of the hits
+//     still unsettled at that point, scored 32 at a time across all of a warp's queries;
+//     finalize_kernel merges the pool into the ordered top-K.
 //   bound pass (bound_kernel, before the scan): starting thresholds at filter speed.
 //
 // The filter only ever discards pairs that provably are not in the exact top-K,
@@ -76,14 +78,14 @@ struct ScanArgs {
     int refresh_every;       // tiles between two looks at the thresholds other CTAs published (an L2 round
                              // trip: every tile for large query tiles, rarer when a tile is only a few queries)
     // per-query exact survivors of every CTA segment, merged by finalize_kernel
-    uint64_t *pool;          // [nq][segs * K] exact keys
+    uint64_t *pool;          // [nq][slab] exact keys
     int32_t *pool_cnt;       // [nq] keys in the pool slab
     int segs;                // slab capacity in segments (scan_segs())
     uint32_t *g_best;        // [nq] orderable score: best known lower bound of the final K-th best
     uint32_t *gslot;         // [nq][nslot] lock-free global feedback: slot (id mod nslot) holds the best exact
                              // score (orderable) any CTA has found among the songs with that residue
     int nslot;               // >= K, multiple of 32
-    unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] inserts
+    unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] refilters; [5..12] cycle counters (-DSR_SCAN_TIMING)
 };
 
 // `stage_bytes`: size of the TMA staging buffer for one song tile (0 for unstaged shapes)
