@@ -636,12 +636,16 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 const int qe = min(32, nql - qb);
                 uint32_t mask = 0;
                 if (DEFER) {
+                    // one funnel shift per query collects the sign of the AND: after qe queries bit
+                    // (qe - 1 - i) of `signs` is SET when none of the thread's songs passed query qb + i
+                    uint32_t signs = 0;
 #pragma unroll 16
                     for (int i = 0; i < qe; ++i) {
                         float2 acc[S / 2];
                         const uint32_t m = filter_query<S>(fp, q0 + qb + i, c.nthr[qb + i], acc);
-                        mask |= ((~m) >> 31) << i;
+                        signs = __funnelshift_l(m, signs, 1);
                     }
+                    mask = __brev(~signs) >> (32 - qe);  // bit i set <=> a song passed query qb + i
                 } else {
 #pragma unroll 2
                     for (int i = 0; i < qe; ++i) {
