@@ -122,8 +122,8 @@ int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k,
  *   "list_ws"   1 (default): the CTAs' top-k lists may live in an L2-resident workspace instead of shared
  *               memory when that keeps the query tile at 256 queries (used for 16 < k <= 72); 0: never
  *   "bound_tiles" layout tiles (2048 songs each) sampled by the threshold bound pass (0 = auto: 48 for k <= 16, else 128)
- *   "trigger_at" a settle phase starts when some hit buffer holds this many ids (0 = cap / 2)
- *   "settle_at" ... and scores and merges every buffer holding at least this many (0 = cap / 16)
+ *   "trigger_at" a settle phase starts when some hit buffer holds this many ids (0 = cap / 4)
+ *   "settle_at" ... and scores and merges every buffer holding at least this many (0 = cap / 32)
  *   "bound"     0: skip the bound pass (threshold bootstrap at filter speed)
  *   "profile"   1: bracket every kernel with CUDA events (read with sr_engine_get_timing)
  *   "reset"     any value: zero the counters and timings below               */
