@@ -15,6 +15,17 @@ exchange, the NCCL all-gather of the per-shard candidates and the merge.
          memory and D2H of the result lists inside the timed region
   roofline / cpu_baseline: see DESIGN.md "measurement"
 
+Every case is followed by a parity check: 32 sampled queries of the last timed batch are compared bit for bit
+(index lists and score bits) with the CPU oracle -- at N > 1 every rank runs the oracle over its own row shard
+and rank 0 merges the parts -- and reported as "parity_check": {"queries": 32, "mismatches": 0}.
+
+Extra keys on the same line (DESIGN.md "measurement"):
+  config3_top100   (N = 1) the same store and batch at top-100 = BASELINE config 3 proper
+  strong_scaling   BASELINE config 4 at every N, including N = 1: 100 M songs TOTAL row-sharded over the N GPUs,
+                   batches of 8192 queries, top-100 ("scaling": "strong"; T_1 / (N T_N) is the efficiency)
+  roofline_hbm_regime, reference_gpu_path (N = 1): the HBM-bound regime of the same kernels, and the
+                   reference's own cuBLAS path rebuilt for sm_100a (oracle/_ref/libref_gpu.so) on BASELINE config 2
+
 `--impl reference` times the reference's own CPU implementation of the path
 (oracle/_ref/libref_cpu.so = unmodified Recommender.cu built with -DDISABLE_CUDA; the
 oracle port when that is absent) with all host threads on a bounded sample of the same
@@ -44,11 +55,25 @@ BYTES_PER_SONG = 48         # 12 x FP32 per song per pass
 METRIC = "song-pairs/s (top-10, 4096-query batches, 10M songs per GPU; queries/s @10M = value / 1e7)"
 
 
+C4_SONGS_TOTAL = 100_000_000   # BASELINE config 4: 100 M songs over the GPUs, 8192 queries, top-100
+C4_BATCH = 8192
+C4_TOPK = 100
+PARITY_QUERIES = 32
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
     except ValueError:
         return default
+
+
+def host_cores() -> int:
+    """Threads this process may use -- NOT OpenMP's default, which torchrun pins to 1 through OMP_NUM_THREADS."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -99,14 +124,14 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline_port(feats: np.ndarray, n_total: int, k: int, budget_s: float = 12.0) -> dict:
+def cpu_baseline_port(feats: np.ndarray, n_total: int, k: int, batch: int, budget_s: float = 12.0) -> dict:
     """The oracle port (oracle/cosine_topk_oracle.c), OpenMP over all host cores, on a
     bounded sample of the batch: `cores` queries per round, rounds until ~budget_s."""
     from oracle_lib import Oracle
     from spotify_recommender_b200 import synth
     o = Oracle()
-    cores = o.max_threads
-    q = synth.query_indices(BATCH, n_total)
+    cores = host_cores()
+    q = synth.query_indices(batch, n_total)
     q = q[q < feats.shape[0]][: max(cores, 8)]
     o.query_index(feats, q[:2], k, threads=cores)  # touch
     done, t0 = 0, time.perf_counter()
@@ -117,7 +142,7 @@ def cpu_baseline_port(feats: np.ndarray, n_total: int, k: int, budget_s: float =
             break
     dt = time.perf_counter() - t0
     return {"value": done * float(feats.shape[0]) / dt, "unit": "song-pairs/s", "cores": cores, "kind": "port",
-            "sample": f"{done} of the batch's {BATCH} queries x {feats.shape[0]} songs, top-{k}, "
+            "sample": f"{done} of the batch's {batch} queries x {feats.shape[0]} songs, top-{k}, "
                       f"oracle/cosine_topk_oracle.c with {cores} OpenMP threads, {dt:.1f} s"}
 
 
@@ -131,15 +156,14 @@ def run_reference(args) -> None:
     n = SONGS_PER_GPU  # one GPU's shard of the workload; the CPU arm does not shard
     feats = synth.features(n)
     qall = synth.query_indices(BATCH, n)
+    cores = host_cores()  # the same at every N: torchrun's OMP_NUM_THREADS=1 does not apply to an explicit thread count
     if Reference.available():
         ref = Reference(feats)
-        cores = int(ref.L.ref_max_threads())
         kind = "reference"
         run = lambda q: ref.batch(q, TOPK, threads=cores)
         what = "oracle/_ref/libref_cpu.so (unmodified reference Recommender.cu, -DDISABLE_CUDA), one recommendByIndex per thread"
     else:
         o = Oracle()
-        cores = o.max_threads
         kind = "port"
         run = lambda q: o.query_index(feats, q, TOPK, threads=cores)
         what = "oracle/cosine_topk_oracle.c (oracle/_ref absent)"
@@ -166,191 +190,370 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+class Job:
+    """One rank's view of the run: device, process group, engine."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from spotify_recommender_b200.engine import Engine
+        self.torch, self.dist = torch, dist
+        self.world = env_int("WORLD_SIZE", 1)
+        self.rank = env_int("RANK", 0)
+        self.local_rank = env_int("LOCAL_RANK", 0)
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        if args.gpus > 1 and self.world == 1:
+            raise SystemExit("for --gpus N > 1 launch with torch.distributed.run --nproc-per-node N (one rank per GPU)")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.eng = Engine(self.local_rank)
+        if args.variant is not None:
+            self.eng.set_option("variant", args.variant)
+        self.stream = torch.cuda.current_stream()
+        props = torch.cuda.get_device_properties(self.dev)
+        self.sm_count = props.multi_processor_count
+        self.peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                self.peaks = json.load(fh)
+        except Exception:
+            pass
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def parity_check(job: Job, feats, n_total: int, lo: int, hi: int, q_last: np.ndarray, out_i, out_s, k: int) -> dict:
+    """PARITY_QUERIES sampled queries of the last timed batch against the CPU oracle, bit for bit.  Every rank
+    scores its own row shard with the oracle (all its share of the host cores); rank 0 merges the parts in the
+    oracle's own order (sr_oracle_merge_parts) and compares with what the GPUs returned."""
+    from oracle_lib import Oracle
+    from spotify_recommender_b200 import synth
+    torch, dist = job.torch, job.dist
+    o = Oracle()
+    nq = q_last.size
+    sel = np.unique(np.linspace(0, nq - 1, PARITY_QUERIES).astype(np.int64))
+    ids = q_last[sel].astype(np.int64)
+    qrows = synth.rows(ids, n_total)
+    ex = np.where((ids >= lo) & (ids < hi), ids - lo, -1).astype(np.int64)
+    threads = max(1, host_cores() // max(1, job.world))
+    t0 = time.perf_counter()
+    li, ls = o.query_rows(feats, qrows, ex, k, id_base=lo, threads=threads)
+    dt = time.perf_counter() - t0
+    if job.world > 1:
+        d_i, d_s = torch.from_numpy(li).to(job.dev), torch.from_numpy(ls).to(job.dev)
+        all_i = torch.empty((job.world,) + tuple(d_i.shape), dtype=torch.int32, device=job.dev)
+        all_s = torch.empty((job.world,) + tuple(d_s.shape), dtype=torch.float32, device=job.dev)
+        dist.all_gather_into_tensor(all_i.view(-1, k), d_i)
+        dist.all_gather_into_tensor(all_s.view(-1, k), d_s)
+        wi, ws = o.merge_parts(all_i.cpu().numpy(), all_s.cpu().numpy())
+    else:
+        wi, ws = li, ls
+    gi = out_i[torch.from_numpy(sel).to(job.dev)].cpu().numpy()
+    gs = out_s[torch.from_numpy(sel).to(job.dev)].cpu().numpy()
+    bad = int(((gi != wi).any(axis=1) | (gs.view(np.uint32) != ws.view(np.uint32)).any(axis=1)).sum())
+    return {"queries": int(sel.size), "mismatches": bad, "top_k": k, "songs": n_total,
+            "oracle": f"oracle/cosine_topk_oracle.c over {'each rank its own row shard, parts merged on rank 0' if job.world > 1 else 'the whole store'}, "
+                      f"{threads} threads per rank, {dt:.2f} s; index lists and score bits compared"}
+
+
+def measure_case(job: Job, args, n_total: int, batch: int, topk: int, steps: int, warmup: int, with_e2e: bool = True,
+                 sample_clocks: bool = False):
+    """Load this rank's row shard of an n_total-song store and time `steps` batches.  Returns (result dict, feats)."""
+    from spotify_recommender_b200 import synth
+    from spotify_recommender_b200.engine import variant_names
+    from spotify_recommender_b200.sharded import ShardedRecommender, shard_bounds
+    torch, eng = job.torch, job.eng
+    sh = ShardedRecommender(eng, n_total, device=job.dev)
+    lo, hi = shard_bounds(n_total, job.world, job.rank)
+    feats = synth.features(n_total, lo, hi)          # this rank's row shard, generated on the host
+    sh.load_shard(feats)
+    n_batches = warmup + steps
+    q_host = [(((np.arange(batch, dtype=np.int64) + b * batch) * 7919 + 13) % n_total).astype(np.int32) for b in range(n_batches)]
+    q_dev = [torch.from_numpy(q).to(job.dev) for q in q_host]
+
+    # ---- device-resident timing ("value") -----------------------------------------------
+    for b in range(warmup):
+        sh.query_by_index_dev(q_dev[b], topk)
+    job.barrier()
+    eng.set_option("profile", 1)
+    eng.set_option("reset", 1)
+    sampler = ClockSampler(job.local_rank) if sample_clocks else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    job.barrier()
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(job.stream)
+    for b in range(warmup, n_batches):
+        out_i, out_s = sh.query_by_index_dev(q_dev[b], topk)
+    ev1.record(job.stream)
+    job.barrier()
+    t_wall1 = time.time()
+    ms_total = job.max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    launches = eng.stat("kernel_launches")
+    scan_ms, scan_n = eng.timing("scan")
+    other = {k: eng.timing(k)[0] / steps for k in ("prep", "sample", "bound", "finalize", "merge")}
+    eng.set_option("profile", 0)
+    out_i, out_s = out_i.clone(), out_s.clone()
+    checksum = int(out_i.to(torch.int64).sum().item())  # the step's result is really read
+    kernel_shape = variant_names()[eng.stat("variant")]
+
+    res = {"songs_total": n_total, "songs_per_gpu": hi - lo, "queries_per_batch": batch, "top_k": topk, "steps": steps,
+           "warmup": warmup, "ms_per_step": ms_total / steps, "value": float(batch) * float(n_total) * steps / (ms_total * 1e-3),
+           "unit": "song-pairs/s", "gpu_launches": launches, "kernel_shape": kernel_shape, "result_checksum": checksum,
+           "clocks": clocks}
+
+    # ---- end to end through the host-buffer API ("e2e") -----------------------------------
+    if with_e2e:
+        sh.query_by_index(q_host[0], topk)
+        job.barrier()
+        t0 = time.perf_counter()
+        for b in range(warmup, n_batches):
+            h_i, h_s = sh.query_by_index(q_host[b], topk)
+        dt = time.perf_counter() - t0
+        job.barrier()
+        e2e_s = job.max_over_ranks(dt)
+        assert int(h_i.astype(np.int64).sum()) == checksum, "host-path and device-path results differ"
+        res["e2e"] = {"value": float(batch) * float(n_total) * steps / e2e_s, "unit": "song-pairs/s",
+                      "h2d_bytes_per_step": batch * 4, "d2h_bytes_per_step": batch * topk * 8, "ms_per_step": 1e3 * e2e_s / steps}
+
+    # ---- roofline of the dominant kernel (scan): FP32-bound for batches beyond Q* = 23 queries (SURVEY 8d) -------
+    sm_max_mhz = float(job.peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+    fp32_peak = job.sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12          # FFMA lanes x 2 flop x max clock
+    pairs_per_launch = float(hi - lo) * batch * steps / max(scan_n, 1)
+    scan_avg_ms = scan_ms / max(scan_n, 1)
+    achieved = FLOP_PER_PAIR * pairs_per_launch / (scan_avg_ms * 1e-3) / 1e12
+    res["roofline"] = {
+        "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+        "kernel": "scan_kernel<%s>" % kernel_shape, "launches_timed": scan_n, "avg_launch_ms": scan_avg_ms,
+        "peak_is": f"{job.sm_count} SMs x 128 FFMA lanes x 2 flop x {sm_max_mhz:.0f} MHz (nominal FP32, no tensor cores; "
+                   "north_star: min(HBM, FP32) roofline; this batch is FP32-bound, Q* = 23)",
+        "algorithmic": f"{FLOP_PER_PAIR} flop/pair x {pairs_per_launch:.3e} pairs per launch",
+        "step_frac": FLOP_PER_PAIR * float(hi - lo) * batch / (ms_total / steps * 1e-3) / 1e12 / fp32_peak,
+        "other_kernels_ms_per_step": other,
+    }
+    res["parity_check"] = parity_check(job, feats, n_total, lo, hi, q_host[-1], out_i, out_s, topk)
+    return res, feats, q_dev
+
+
+def hbm_regime(job: Job, q_dev, n_local: int, topk: int) -> dict:
+    """The HBM-bound regime of the same kernels (Q < Q* = 23 queries: one pass over the store per call)."""
+    torch, eng = job.torch, job.eng
+    try:
+        hbm_peak = float(job.peaks.get("hbm_gbs") or 6650.0)
+        hbm = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
+               "peak_is": "MEASURED_PEAKS.json hbm_gbs" if job.peaks.get("hbm_gbs") else "fallback 6650 GB/s",
+               "algorithmic": f"{BYTES_PER_SONG} B/song x {n_local} songs per call", "cases": []}
+        for nq_small in (1, 4, 16):
+            qs = q_dev[0][:nq_small].contiguous()
+            os_ = torch.empty((nq_small, topk), dtype=torch.int32, device=job.dev)
+            for _ in range(3):
+                eng.query_by_index_dev(qs, nq_small, topk, os_, None, job.stream.cuda_stream)
+            torch.cuda.synchronize()
+            eng.set_option("profile", 1)
+            eng.set_option("reset", 1)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(job.stream)
+            for _ in range(20):
+                eng.query_by_index_dev(qs, nq_small, topk, os_, None, job.stream.cuda_stream)
+            b_.record(job.stream)
+            torch.cuda.synchronize()
+            t_scan = eng.timing("scan")[0] / 20 * 1e-3
+            eng.set_option("profile", 0)
+            # the call as a user issues it: no per-kernel event brackets in the stream
+            for _ in range(3):
+                eng.query_by_index_dev(qs, nq_small, topk, os_, None, job.stream.cuda_stream)
+            torch.cuda.synchronize()
+            a.record(job.stream)
+            for _ in range(50):
+                eng.query_by_index_dev(qs, nq_small, topk, os_, None, job.stream.cuda_stream)
+            b_.record(job.stream)
+            torch.cuda.synchronize()
+            t_call = a.elapsed_time(b_) / 50 * 1e-3
+            nbytes = BYTES_PER_SONG * float(n_local)
+            hbm["cases"].append({"queries": nq_small, "ms_per_call": t_call * 1e3, "scan_kernel_ms": t_scan * 1e3,
+                                 "achieved_call": nbytes / t_call / 1e9, "frac_call": nbytes / t_call / 1e9 / hbm_peak,
+                                 "achieved_scan_kernel": nbytes / t_scan / 1e9,
+                                 "frac_scan_kernel": nbytes / t_scan / 1e9 / hbm_peak})
+        return hbm
+    except Exception as exc:  # never lose the headline over the side measurement
+        return {"error": str(exc)}
+
+
+def reference_gpu_path(job: Job) -> dict:
+    """BASELINE config 2 (1 M songs, 1024 queries, top-10, host buffers) on this engine and on the reference's own GPU
+    path -- the unmodified Recommender.cu rebuilt for sm_100a (oracle/_ref/libref_gpu.so): cuBLAS SGEMV + two kernels
+    + D2H + host heap per query (Recommender.cu:184-254, :293-315); its batch mode is sequential calls, timed on a
+    bounded sample of the batch."""
+    try:
+        from oracle_lib import Reference
+        from spotify_recommender_b200 import synth
+        from spotify_recommender_b200.engine import Engine
+        if not Reference.available(gpu=True):
+            return {"unavailable": "oracle/_ref/libref_gpu.so not built"}
+        n, nq, k, sample = 1_000_000, 1024, 10, 64
+        f = synth.features(n)
+        q = synth.query_indices(nq, n)
+        with Engine(job.local_rank) as e2:
+            e2.load_features(f)
+            for _ in range(3):
+                gi, _ = e2.query_by_index(q, k)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                gi, _ = e2.query_by_index(q, k)
+            t_ours = (time.perf_counter() - t0) / 10
+        ref = Reference(f, gpu=True)
+        if not ref.gpu_enabled():
+            return {"unavailable": "the reference fell back to its CPU path"}
+        ref.batch(q[:8], k)
+        t0 = time.perf_counter()
+        ri = ref.batch(q[:sample], k)
+        t_ref = (time.perf_counter() - t0) / sample
+        ref.close()
+        same = int((ri == gi[:sample]).all(axis=1).sum())
+        return {"config": f"{n} songs x 12, {nq} queries, top-{k}, host buffers in and out",
+                "ours_ms_per_batch": t_ours * 1e3, "ours_ms_per_query": t_ours * 1e3 / nq,
+                "reference_ms_per_query": t_ref * 1e3, "reference_ms_per_batch_extrapolated": t_ref * 1e3 * nq,
+                "reference_sample": f"{sample} sequential recommendByIndex calls of the batch's {nq}",
+                "speedup_per_batch": t_ref * nq / t_ours, "identical_ordered_lists": f"{same}/{sample}"}
+    except Exception as exc:
+        return {"error": str(exc)}
+
+
 def run_ours(args) -> None:
     global BATCH, TOPK
     if args.batch:
         BATCH = args.batch
     if args.topk:
         TOPK = args.topk
-    import torch
-    import torch.distributed as dist
-    from spotify_recommender_b200 import synth
-    from spotify_recommender_b200.engine import Engine, variant_names
-    from spotify_recommender_b200.sharded import ShardedRecommender, shard_bounds
-
-    world = env_int("WORLD_SIZE", 1)
-    rank = env_int("RANK", 0)
-    local_rank = env_int("LOCAL_RANK", 0)
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.gpus > 1 and world == 1:
-        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run --nproc-per-node N (one rank per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    job = Job(args)
+    world, rank = job.world, job.rank
     n_total = int(args.songs_total) if args.songs_total else SONGS_PER_GPU * world
-    eng = Engine(local_rank)
-    if args.variant is not None:
-        eng.set_option("variant", args.variant)
-    sh = ShardedRecommender(eng, n_total, device=dev)
-    lo, hi = shard_bounds(n_total, world, rank)
-    feats = synth.features(n_total, lo, hi)          # this rank's row shard, generated on the host
-    sh.load_shard(feats)
-    n_batches = args.warmup + args.steps
-    q_host = [((np.arange(BATCH, dtype=np.int64) + b * BATCH) * 7919 + 13) % n_total for b in range(n_batches)]
-    q_host = [q.astype(np.int32) for q in q_host]
-    q_dev = [torch.from_numpy(q).to(dev) for q in q_host]
-    stream = torch.cuda.current_stream()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ("value") -----------------------------------------------
-    for b in range(args.warmup):
-        sh.query_by_index_dev(q_dev[b], TOPK)
-    barrier()
-    eng.set_option("profile", 1)
-    eng.set_option("reset", 1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
-    barrier()
-    t_wall0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for b in range(args.warmup, n_batches):
-        out_i, out_s = sh.query_by_index_dev(q_dev[b], TOPK)
-    ev1.record(stream)
-    barrier()
-    t_wall1 = time.time()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    clocks = sampler.stop(t_wall0, t_wall1)
-    launches = eng.stat("kernel_launches")
-    scan_ms, scan_n = eng.timing("scan")
-    other = {k: eng.timing(k)[0] / args.steps for k in ("prep", "sample", "bound", "finalize", "merge")}
-    eng.set_option("profile", 0)
-    checksum = int(out_i.to(torch.int64).sum().item())  # the step's result is really read
-
-    # ---- end to end through the host-buffer API ("e2e") -----------------------------------
-    sh.query_by_index(q_host[0], TOPK)
-    barrier()
-    t0 = time.perf_counter()
-    for b in range(args.warmup, n_batches):
-        h_i, h_s = sh.query_by_index(q_host[b], TOPK)
-    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    barrier()
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_s = float(t_e2e.item())
-    assert int(h_i.astype(np.int64).sum()) == checksum, "host-path and device-path results differ"
-
-    pairs_per_step = float(BATCH) * float(n_total)
-    value = pairs_per_step * args.steps / (ms_total * 1e-3)
-    e2e_value = pairs_per_step * args.steps / e2e_s
-
-    # ---- roofline of the dominant kernel (scan): FP32-bound at Q = 4096 ----------
-    props = torch.cuda.get_device_properties(dev)
-    sm_count = props.multi_processor_count
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except Exception:
-        pass
-    sm_max_mhz = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
-    fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12          # FFMA lanes x 2 flop x max clock
-    pairs_per_launch = float(hi - lo) * BATCH * args.steps / max(scan_n, 1)
-    scan_avg_ms = scan_ms / max(scan_n, 1)
-    achieved = FLOP_PER_PAIR * pairs_per_launch / (scan_avg_ms * 1e-3) / 1e12
-    traffic = None
+    main, feats, q_dev = measure_case(job, args, n_total, BATCH, TOPK, args.steps, args.warmup, sample_clocks=True)
+    n_local = main["songs_per_gpu"]
+    roofline = main["roofline"]
+    # DRAM traffic of one scan launch: a STORED figure from the committed ncu --set full capture of this command
+    # (profiles/scan_kernel_summary.json), not measured in this run -- ncu cannot run inside the timed program
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "scan_kernel_summary.json")) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_launch")
+            summ = json.load(fh)
+        traffic = summ.get("dram_bytes_per_launch")
+        traffic_src = f"stored: ncu --set full capture {summ.get('source', 'profiles/scan_kernel_summary.json')} (dram__bytes_read.sum + dram__bytes_write.sum of one launch)"
     except Exception:
         pass
-    kernel_shape = variant_names()[eng.stat("variant")]  # of the timed batches (the HBM sweep below uses another)
-    roofline = {
-        "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-        "traffic": traffic, "kernel": "scan_kernel<%s>" % kernel_shape,
-        "launches_timed": scan_n, "avg_launch_ms": scan_avg_ms,
-        "peak_is": f"{sm_count} SMs x 128 FFMA lanes x 2 flop x {sm_max_mhz:.0f} MHz (nominal FP32, no tensor cores; "
-                   "north_star: min(HBM, FP32) roofline; this batch is FP32-bound, Q* = 23)",
-        "peak_measured_ffma2": eng.measure_fp32(1),
-        "algorithmic": f"{FLOP_PER_PAIR} flop/pair x {pairs_per_launch:.3e} pairs per launch",
-        "other_kernels_ms_per_step": other,
-    }
-    # the HBM-bound regime of the same kernels (Q < Q* = 23 queries: one pass over the store per call)
-    hbm = None
-    if rank == 0 and world == 1:
-        try:
-            hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
-            hbm = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
-                   "peak_is": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6650 GB/s",
-                   "algorithmic": f"{BYTES_PER_SONG} B/song x {hi - lo} songs per call", "cases": []}
-            for nq_small in (1, 4, 16):
-                qs = q_dev[0][:nq_small].contiguous()
-                os_ = torch.empty((nq_small, TOPK), dtype=torch.int32, device=dev)
-                for _ in range(3):
-                    eng.query_by_index_dev(qs, nq_small, TOPK, os_, None, stream.cuda_stream)
-                torch.cuda.synchronize()
-                eng.set_option("profile", 1)
-                eng.set_option("reset", 1)
-                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                for _ in range(20):
-                    eng.query_by_index_dev(qs, nq_small, TOPK, os_, None, stream.cuda_stream)
-                b_.record(stream)
-                torch.cuda.synchronize()
-                t_call = a.elapsed_time(b_) / 20 * 1e-3
-                t_scan = eng.timing("scan")[0] / 20 * 1e-3
-                eng.set_option("profile", 0)
-                nbytes = BYTES_PER_SONG * float(hi - lo)
-                hbm["cases"].append({"queries": nq_small, "ms_per_call": t_call * 1e3, "scan_kernel_ms": t_scan * 1e3,
-                                     "achieved_call": nbytes / t_call / 1e9, "frac_call": nbytes / t_call / 1e9 / hbm_peak,
-                                     "achieved_scan_kernel": nbytes / t_scan / 1e9,
-                                     "frac_scan_kernel": nbytes / t_scan / 1e9 / hbm_peak})
-        except Exception as exc:  # never lose the headline over the side measurement
-            hbm = {"error": str(exc)}
+    roofline["traffic"] = traffic
+    roofline["traffic_source"] = traffic_src
+    roofline["peak_measured_ffma2"] = job.eng.measure_fp32(1)
 
+    single = rank == 0 and world == 1
+    top100 = None
+    if single and not args.quick and TOPK != 100:
+        # BASELINE config 3 proper: the same store and batch, top-100
+        job.eng.set_option("reset", 1)
+        from spotify_recommender_b200 import synth  # noqa: F401
+        top100 = measure_top100(job, args, n_total, feats)
+    hbm = hbm_regime(job, q_dev, n_local, TOPK) if single else None
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_port(feats, n_total, TOPK)
+    if single and not args.no_cpu_baseline:
+        cpu = cpu_baseline_port(feats, n_total, TOPK, BATCH)
+    del feats, q_dev
+    refgpu = reference_gpu_path(job) if single and not args.quick else None
+
+    strong = None
+    if not args.quick and not args.songs_total:
+        st_steps = max(2, min(args.steps, 5))
+        c4, f4, q4 = measure_case(job, args, C4_SONGS_TOTAL, C4_BATCH, C4_TOPK, st_steps, 3)
+        del f4, q4
+        strong = {"scaling": "strong", "n_gpus": world, "value": c4["value"], "unit": c4["unit"], "ms_per_step": c4["ms_per_step"],
+                  "steps": st_steps, "warmup": 3,
+                  "config": {"workload": f"BASELINE config 4: {C4_SONGS_TOTAL} songs TOTAL x 12 row-sharded over {world} GPU(s) "
+                                         f"({c4['songs_per_gpu']} per GPU), batch of {C4_BATCH} in-store queries, exact top-{C4_TOPK}",
+                             "parallelism": f"row-shard x{world}" + (" + one NCCL all-gather of packed keys + merge" if world > 1 else "")},
+                  "e2e": c4.get("e2e"), "roofline": {k: c4["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "step_frac", "avg_launch_ms", "other_kernels_ms_per_step")},
+                  "parity_check": c4["parity_check"], "gpu_launches": c4["gpu_launches"],
+                  "efficiency_is": "T(n_gpus = 1) / (n_gpus x T(n_gpus)) over the ms_per_step of this key at each N"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "song-pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": main["value"], "unit": "song-pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{hi - lo} songs x 12 features per GPU ({n_total} total, row-sharded), "
+            "config": {"workload": f"{n_local} songs x 12 features per GPU ({n_total} total, row-sharded), "
                                    f"batch of {BATCH} in-store queries, exact top-{TOPK}",
-                       "songs_total": n_total, "songs_per_gpu": hi - lo, "queries_per_batch": BATCH,
-                       "top_k": TOPK, "parallelism": f"row-shard x{world}" + (" + NCCL all-gather + merge" if world > 1 else ""),
+                       "songs_total": n_total, "songs_per_gpu": n_local, "queries_per_batch": BATCH,
+                       "top_k": TOPK, "parallelism": f"row-shard x{world}" + (" + one NCCL all-gather of packed keys + merge" if world > 1 else ""),
                        "l2": "store (2 x 480 MB per GPU) is larger than the 126 MB L2; every step uses a fresh query batch",
-                       "kernel_shape": kernel_shape},
-            "queries_per_s_at_10M": value / 1e7,
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "song-pairs/s", "h2d_bytes_per_step": BATCH * 4,
-                    "d2h_bytes_per_step": BATCH * TOPK * 8, "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": launches,
+                       "kernel_shape": main["kernel_shape"]},
+            "queries_per_s_at_10M": main["value"] / 1e7,
+            "clocks": main["clocks"],
+            "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"],
             "roofline": roofline,
+            "parity_check": main["parity_check"],
+            "config3_top100": top100,
+            "strong_scaling": strong,
             "roofline_hbm_regime": hbm,
+            "reference_gpu_path": refgpu,
             "cpu_baseline": cpu,
-            "result_checksum": checksum,
+            "result_checksum": main["result_checksum"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    eng.close()
+        job.dist.barrier()
+        job.dist.destroy_process_group()
+    job.eng.close()
+
+
+def measure_top100(job: Job, args, n_total: int, feats) -> dict:
+    """The loaded store again at top-100 (BASELINE config 3 proper), device-resident timing + parity."""
+    torch, eng = job.torch, job.eng
+    steps, warmup, k = max(2, min(args.steps, 10)), 3, 100
+    q_host = [(((np.arange(BATCH, dtype=np.int64) + b * BATCH) * 7919 + 13) % n_total).astype(np.int32) for b in range(warmup + steps)]
+    q_dev = [torch.from_numpy(q).to(job.dev) for q in q_host]
+    oi = torch.empty((BATCH, k), dtype=torch.int32, device=job.dev)
+    os_ = torch.empty((BATCH, k), dtype=torch.float32, device=job.dev)
+    for b in range(warmup):
+        eng.query_by_index_dev(q_dev[b], BATCH, k, oi, os_, job.stream.cuda_stream)
+    torch.cuda.synchronize()
+    eng.set_option("profile", 1)
+    eng.set_option("reset", 1)
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(job.stream)
+    for b in range(warmup, warmup + steps):
+        eng.query_by_index_dev(q_dev[b], BATCH, k, oi, os_, job.stream.cuda_stream)
+    b_.record(job.stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b_) / steps
+    scan_ms, scan_n = eng.timing("scan")
+    other = {kk: eng.timing(kk)[0] / steps for kk in ("prep", "sample", "bound", "finalize")}
+    eng.set_option("profile", 0)
+    sm_max_mhz = float(job.peaks.get("sm_max_mhz") or 1965.0)
+    fp32_peak = job.sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    flop_step = FLOP_PER_PAIR * float(n_total) * BATCH
+    return {"workload": f"{n_total} songs, batch of {BATCH} queries, exact top-{k} (BASELINE config 3)", "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "value": float(n_total) * BATCH / (ms * 1e-3), "unit": "song-pairs/s",
+            "roofline": {"bound": "fp32", "peak": fp32_peak, "unit": "TFLOP/s", "frac": flop_step / (scan_ms / steps * 1e-3) / 1e12 / fp32_peak,
+                         "step_frac": flop_step / (ms * 1e-3) / 1e12 / fp32_peak, "avg_launch_ms": scan_ms / max(scan_n, 1),
+                         "launches_timed": scan_n, "other_kernels_ms_per_step": other},
+            "parity_check": parity_check(job, feats, n_total, 0, n_total, q_host[-1], oi, os_, k)}
 
 
 def main() -> None:
@@ -361,6 +564,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--variant", type=int, default=None, help="scan kernel shape (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="development: the headline case only (no top-100, config 4, reference GPU path)")
     ap.add_argument("--songs-total", type=float, default=None,
                     help="non-contract runs: total songs, row-sharded over the GPUs (e.g. 1e8 for BASELINE config 4)")
     ap.add_argument("--batch", type=int, default=None, help="non-contract runs: queries per batch")

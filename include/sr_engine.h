@@ -18,7 +18,10 @@
  *   - results are ordered by (score descending, id ascending); rows shorter
  *     than k are padded with id -1 / score 0.  Scores are bit-identical to the
  *     reference's CPU arithmetic (Recommender.cu:256-273).
- *   - 1 <= k <= 1024.
+ *   - any k >= 1: like the reference (Recommender.cu:300-315) a query yields
+ *     min(k, songs - 1) results.  Lists longer than 1024 are produced 1024 at a
+ *     time (one more pass over the store each, every pass continuing below the
+ *     last key of the one before).
  */
 #ifndef SR_ENGINE_H
 #define SR_ENGINE_H
@@ -85,7 +88,10 @@ int sr_engine_query_by_vector(sr_engine *e, const float *qrows, const int32_t *e
  * device, work is enqueued on `stream` and NOT synchronised.  `stream` is a
  * cudaStream_t (NULL = CUDA's legacy default stream, as everywhere in CUDA) or
  * SR_ENGINE_OWN_STREAM for the engine's own non-blocking stream.  Used by the multi-GPU host (torch owns the
- * buffers and the NCCL exchange) and by bench.py's kernel-only timing. */
+ * buffers and the NCCL exchange) and by bench.py's kernel-only timing.
+ * A query id the store does not own cannot be refused before the work is enqueued: its result row is
+ * -1 / 0 and the engine remembers it -- the next sr_engine_synchronize() (or any host-buffer call) returns
+ * SR_EINVAL, and sr_engine_get_stat("bad_index") reads and clears the flag. */
 int sr_engine_query_by_index_dev(sr_engine *e, const int32_t *d_qidx, int nq, int k,
                                  int32_t *d_out_idx, float *d_out_score, void *stream);
 int sr_engine_query_by_vector_dev(sr_engine *e, const float *d_qrows, const int32_t *d_exclude,
@@ -99,6 +105,21 @@ int sr_engine_query_by_vector_dev(sr_engine *e, const float *d_qrows, const int3
 int sr_engine_merge_topk_dev(sr_engine *e, const int32_t *d_idx, const float *d_score,
                              int parts, int nq, int k, int32_t *d_out_idx, float *d_out_score,
                              void *stream);
+
+/* The same local scoring with the result in the EXCHANGE FORMAT of the row-sharded path: one packed 64-bit key per
+ * candidate (orderable score << 32 | ~id; 0 = none), nq x k, so that a step needs exactly one all-gather.
+ * d_ceil is NULL or nq keys: only candidates ordered strictly after d_ceil[q] are admitted (how a list longer
+ * than 1024 continues across shards).  1 <= k <= 1024. */
+int sr_engine_query_keys_by_vector_dev(sr_engine *e, const float *d_qrows, const int32_t *d_exclude,
+                                       int nq, int k, const uint64_t *d_ceil, uint64_t *d_out_keys,
+                                       void *stream);
+
+/* Merge of `parts` gathered key lists (parts x nq x k, as one NCCL all-gather of the buffers above delivers
+ * them) into columns [col, col + k) of the nq x stride result rows; d_ceil_out (or NULL) receives each
+ * query's k-th key (0 when fewer than k candidates exist).  stride <= 0 means k. */
+int sr_engine_merge_keys_dev(sr_engine *e, const uint64_t *d_keys, int parts, int nq, int k,
+                             int32_t *d_out_idx, float *d_out_score, int stride, int col,
+                             uint64_t *d_ceil_out, void *stream);
 
 /* First step of the row-sharded multi-GPU path: d_out (count x 12) receives the raw
  * feature rows (Song::features, Song.h:26) of the global ids this engine owns and
@@ -120,7 +141,8 @@ int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k,
  *   "sample"    threshold-bootstrap sample size per query (0 = off, else power of two <= 4096)
  *   "hit_cap"   hit-buffer entries per query per CTA (multiple of 32; 0 = sized from k)
  *   "list_ws"   1 (default): the CTAs' top-k lists may live in an L2-resident workspace instead of shared
- *               memory when that keeps the query tile at 256 queries (used for 16 < k <= 72); 0: never
+ *               memory when that keeps the query tile at 256 queries (used for 16 < k <= "list_ws_kmax"); 0: never
+ *   "small_max" batches of at most this many queries take the TMA-staged small-batch kernel shape
  *   "bound_tiles" layout tiles (2048 songs each) sampled by the threshold bound pass (0 = auto: 48 for k <= 16, else 128)
  *   "trigger_at" a settle phase starts when some hit buffer holds this many ids (0 = cap / 4)
  *   "settle_at" ... and scores and merges every buffer holding at least this many (0 = cap / 32)
@@ -132,7 +154,8 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value);
 /* Counters since create()/reset (synchronises the engine's stream):
  * "kernel_launches", "queries", "filter_hits", "settles", "rescans", "refilters", "rescored",
  * "irregular_songs", "sm_count", "scan_grid", "scan_tile_songs", "device_bytes",
- * "variant" (the shape the last pass used), "qt". */
+ * "variant" (the shape the last pass used), "qt", "lists_in_smem" (of the last pass), "bad_index"
+ * (reads and clears the flag described above). */
 int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value);
 
 /* With "profile" on: total device milliseconds and launch count of one kernel
@@ -175,8 +198,35 @@ int sr_engine_normalize_features_dev(sr_engine *e, const float *d_raw11, const i
  * sorted (byte-wise) order -- deterministic whatever the order of the rows. */
 int sr_genre_ids(const char *const *names, int64_t n, int mode, int32_t *ids, int32_t *n_genres);
 
-/* Blocks until everything enqueued on the engine's own stream has finished. */
+/* Blocks until everything enqueued on the engine's own stream has finished; returns SR_EINVAL if a
+ * device-pointer call since the last check met a query id the store does not own. */
 int sr_engine_synchronize(sr_engine *e);
+
+/* ---- several GPUs behind one handle, in ONE process (the reference itself is hard-wired to
+ * device 0, Recommender.cu:124).  This is what include/sr_recommender.hpp uses when more than one sm_100
+ * device is visible, so the reference's C++ host reaches the whole box without Python or MPI.
+ *
+ *   devices / n_devices   CUDA ordinals, one shard each (NULL / 0: every visible device).  An ordinal may
+ *                         repeat -- several shards on one GPU -- which is how the path is tested on one GPU.
+ *   load_features         replicate == 0: rows are split into contiguous row shards (shard s owns
+ *                         [s * ceil(n / G), ...)), queries visit every shard, the shards' top-k key lists are
+ *                         merged by one kernel that reads them over NVLink peer access (north_star (4));
+ *                         replicate != 0: every shard holds all rows and serves a slice of the QUERIES
+ *                         (BASELINE config 5: all-pairs).
+ *   query_by_index        as sr_engine_query_by_index, ids global in [0, n); any k >= 1.
+ *   all_pairs_topk        the n x k neighbour table (HOST), every song a query.
+ * Results are identical, bit for bit, whatever the number of shards. */
+typedef struct sr_sharded sr_sharded;
+int sr_sharded_create(sr_sharded **out, const int *devices, int n_devices);
+void sr_sharded_destroy(sr_sharded *s);
+const char *sr_sharded_last_error(const sr_sharded *s);
+int sr_sharded_load_features(sr_sharded *s, const float *rows, int64_t n, int replicate);
+int64_t sr_sharded_song_count(const sr_sharded *s);
+int sr_sharded_shard_count(const sr_sharded *s);
+sr_engine *sr_sharded_engine(sr_sharded *s, int shard); /* for set_option / get_stat */
+int sr_sharded_query_by_index(sr_sharded *s, const int32_t *qidx, int nq, int k,
+                              int32_t *out_idx, float *out_score);
+int sr_sharded_all_pairs_topk(sr_sharded *s, int k, int32_t *out_idx, float *out_score);
 
 #ifdef __cplusplus
 }

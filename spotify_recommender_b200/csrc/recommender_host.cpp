@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -16,13 +17,24 @@
 #include "sr_engine.h"
 
 struct Recommender::Impl {
-    sr_engine *engine = nullptr;
+    sr_engine *engine = nullptr;     // one GPU ...
+    sr_sharded *sharded = nullptr;   // ... or a row-sharded store over several
     // query resolution indexes: first occurrence wins, as the reference's
     // linear scans return the first match (Recommender.cu:320-327, :336-354)
     std::unordered_map<std::string, int> by_id;
     std::unordered_map<std::string, int> by_lower_name;
-    std::string lower_blob;            // all lower-cased names, '\0'-separated
-    std::vector<uint32_t> lower_off;   // start of name i in lower_blob (size n+1)
+    std::string lower_blob;            // all lower-cased names, '\0'-separated (a '\0' inside a name is stored as '\1')
+    std::vector<size_t> lower_off;     // start of name i in lower_blob (size n+1)
+    void reset_index(size_t n)
+    {
+        by_id.clear();
+        by_lower_name.clear();
+        lower_blob.clear();
+        lower_off.assign(1, (size_t)0);
+        by_id.reserve(n * 2);
+        by_lower_name.reserve(n * 2);
+    }
+    void index_song(size_t i, const std::string &id, const std::string &name);
 };
 
 namespace {
@@ -32,7 +44,38 @@ std::string lower(const std::string &s)
     std::transform(r.begin(), r.end(), r.begin(), [](unsigned char c) { return (char)std::tolower(c); });
     return r;
 }
+// Which GPUs serve the store.  SR_DEVICES="0,1,2,3" (ordinals, may repeat) decides; without it a store of at
+// least 20 M songs is row-sharded over every visible device and anything smaller stays on the current one.
+std::vector<int> pick_devices(long long count)
+{
+    std::vector<int> dev;
+    if (const char *env = std::getenv("SR_DEVICES")) {
+        for (const char *p = env; *p;) {
+            char *end = nullptr;
+            long v = std::strtol(p, &end, 10);
+            if (end == p) break;
+            dev.push_back((int)v);
+            p = (*end == ',') ? end + 1 : end;
+        }
+        return dev;
+    }
+    if (count >= 20000000LL) return dev;  // empty = "every visible device", resolved by sr_sharded_create
+    dev.push_back(-1);                    // the current device
+    return dev;
+}
 }  // namespace
+
+void Recommender::Impl::index_song(size_t i, const std::string &id, const std::string &name)
+{
+    by_id.emplace(id, (int)i);  // emplace keeps the first
+    std::string l = lower(name);
+    by_lower_name.emplace(l, (int)i);
+    for (char &ch : l)
+        if (ch == '\0') ch = '\1';  // keep "a hit lies inside one name" true for the substring scan
+    lower_blob.append(l);
+    lower_blob.push_back('\0');
+    lower_off.push_back(lower_blob.size());
+}
 
 Recommender::Recommender() : initialized(false), numSongs(0), gpuEnabled(false), impl(new Impl()) {}
 
@@ -40,6 +83,7 @@ Recommender::~Recommender()
 {
     if (impl) {
         if (impl->engine) sr_engine_destroy(impl->engine);
+        if (impl->sharded) sr_sharded_destroy(impl->sharded);
         delete impl;
     }
 }
@@ -54,17 +98,32 @@ bool Recommender::initializeDense(const float *features, long long count)
         std::cerr << "Error: too many songs for 32-bit song indices: " << count << std::endl;
         return false;
     }
-    if (!impl->engine) {
-        if (sr_engine_create(&impl->engine, -1) != SR_OK) {
+    const std::vector<int> dev = pick_devices(count);
+    const bool want_sharded = dev.size() != 1;
+    if (impl->engine && want_sharded) { sr_engine_destroy(impl->engine); impl->engine = nullptr; }
+    if (impl->sharded && !want_sharded) { sr_sharded_destroy(impl->sharded); impl->sharded = nullptr; }
+    if (want_sharded) {
+        if (!impl->sharded && sr_sharded_create(&impl->sharded, dev.empty() ? nullptr : dev.data(), (int)dev.size()) != SR_OK) {
+            std::cerr << "Error: GPU engines unavailable: " << sr_sharded_last_error(nullptr)
+                      << " (no CPU fallback in this build)" << std::endl;
+            impl->sharded = nullptr;
+            return false;
+        }
+        if (sr_sharded_load_features(impl->sharded, features, count, 0) != SR_OK) {
+            std::cerr << "Error: failed to upload features: " << sr_sharded_last_error(impl->sharded) << std::endl;
+            return false;
+        }
+    } else {
+        if (!impl->engine && sr_engine_create(&impl->engine, dev[0]) != SR_OK) {
             std::cerr << "Error: GPU engine unavailable: " << sr_engine_last_error(nullptr)
                       << " (no CPU fallback in this build)" << std::endl;
             impl->engine = nullptr;
             return false;
         }
-    }
-    if (sr_engine_load_features(impl->engine, features, count, 0) != SR_OK) {
-        std::cerr << "Error: failed to upload features: " << sr_engine_last_error(impl->engine) << std::endl;
-        return false;
+        if (sr_engine_load_features(impl->engine, features, count, 0) != SR_OK) {
+            std::cerr << "Error: failed to upload features: " << sr_engine_last_error(impl->engine) << std::endl;
+            return false;
+        }
     }
     numSongs = (int)count;
     initialized = true;
@@ -128,12 +187,7 @@ bool Recommender::initializeFromFile(const std::string &binaryPath)
     }
     const size_t n = (size_t)numSongs;
     std::vector<float> dense(n * FEATURE_COUNT);
-    impl->by_id.clear();
-    impl->by_lower_name.clear();
-    impl->lower_blob.clear();
-    impl->lower_off.assign(1, 0u);
-    impl->by_id.reserve(n * 2);
-    impl->by_lower_name.reserve(n * 2);
+    impl->reset_index(n);
     std::string id, name;
     for (size_t i = 0; i < n && cur.ok; ++i) {  // Song::serialize order (Song.h:35-54)
         int32_t genre;
@@ -143,12 +197,7 @@ bool Recommender::initializeFromFile(const std::string &binaryPath)
         cur.take(&genre, sizeof genre);
         cur.take(&dense[i * FEATURE_COUNT], sizeof(float) * FEATURE_COUNT);
         if (!cur.ok) break;
-        impl->by_id.emplace(id, (int)i);
-        std::string l = lower(name);
-        impl->by_lower_name.emplace(l, (int)i);
-        impl->lower_blob.append(l);
-        impl->lower_blob.push_back('\0');
-        impl->lower_off.push_back((uint32_t)impl->lower_blob.size());
+        impl->index_song(i, id, name);
     }
     if (!cur.ok) {
         std::cerr << "Error: " << binaryPath << " is truncated or corrupt" << std::endl;
@@ -172,20 +221,8 @@ bool Recommender::initialize(const std::vector<Song> &songs)
     // AoS -> dense row-major n x 12 (what Recommender.cu:162-166 packs), then one upload
     std::vector<float> dense(n * FEATURE_COUNT);
     for (size_t i = 0; i < n; ++i) std::memcpy(&dense[i * FEATURE_COUNT], songs[i].features, sizeof(float) * FEATURE_COUNT);
-    impl->by_id.clear();
-    impl->by_lower_name.clear();
-    impl->lower_blob.clear();
-    impl->lower_off.assign(1, 0u);
-    impl->by_id.reserve(n * 2);
-    impl->by_lower_name.reserve(n * 2);
-    for (size_t i = 0; i < n; ++i) {
-        impl->by_id.emplace(songs[i].track_id, (int)i);  // emplace keeps the first
-        std::string l = lower(songs[i].track_name);
-        impl->by_lower_name.emplace(l, (int)i);
-        impl->lower_blob.append(l);
-        impl->lower_blob.push_back('\0');
-        impl->lower_off.push_back((uint32_t)impl->lower_blob.size());
-    }
+    impl->reset_index(n);
+    for (size_t i = 0; i < n; ++i) impl->index_song(i, songs[i].track_id, songs[i].track_name);
     if (!initializeDense(dense.data(), (long long)n)) return false;
     std::cout << "Recommender initialized on GPU: " << numSongs << " songs resident" << std::endl;
     return true;
@@ -205,12 +242,16 @@ std::vector<std::vector<Recommendation> > Recommender::recommendBatch(const std:
             return out;
         }
     }
-    const int k = std::min(topN, 1024);
+    // like the reference (Recommender.cu:300-315) a query yields min(topN, songs - 1) results, whatever topN
+    const int k = std::max(1, std::min(topN, numSongs - 1));
     std::vector<int32_t> qi(idx.begin(), idx.end());
     std::vector<int32_t> oi(qi.size() * (size_t)k);
     std::vector<float> os(qi.size() * (size_t)k);
-    if (sr_engine_query_by_index(impl->engine, qi.data(), (int)qi.size(), k, oi.data(), os.data()) != SR_OK) {
-        std::cerr << "Error: GPU query failed: " << sr_engine_last_error(impl->engine) << std::endl;
+    const int rc = impl->sharded ? sr_sharded_query_by_index(impl->sharded, qi.data(), (int)qi.size(), k, oi.data(), os.data())
+                                 : sr_engine_query_by_index(impl->engine, qi.data(), (int)qi.size(), k, oi.data(), os.data());
+    if (rc != SR_OK) {
+        std::cerr << "Error: GPU query failed: "
+                  << (impl->sharded ? sr_sharded_last_error(impl->sharded) : sr_engine_last_error(impl->engine)) << std::endl;
         return out;
     }
     out.resize(qi.size());
@@ -252,11 +293,13 @@ int Recommender::findSongByName(const std::string &trackName) const
     const std::string &blob = impl->lower_blob;
     const size_t n = impl->lower_off.size() - 1;
     if (q.empty()) return n ? 0 : -1;
-    if (q.find('\0') != std::string::npos) return -1;
-    size_t pos = blob.find(q);
+    std::string needle = q;
+    for (char &ch : needle)
+        if (ch == '\0') ch = '\1';  // as the blob stores it
+    size_t pos = blob.find(needle);
     if (pos == std::string::npos) return -1;
-    // names are '\0'-separated and q has no '\0', so a hit lies inside one name
-    size_t i = std::upper_bound(impl->lower_off.begin(), impl->lower_off.end(), (uint32_t)pos) - impl->lower_off.begin() - 1;
+    // names are '\0'-separated and the needle has no '\0', so a hit lies inside one name
+    size_t i = std::upper_bound(impl->lower_off.begin(), impl->lower_off.end(), pos) - impl->lower_off.begin() - 1;
     return i < n ? (int)i : -1;
 }
 

@@ -67,19 +67,44 @@ struct PrepArgs {
     int32_t *excl;
     int32_t *pool_cnt;        // per-query state, reset here
     uint32_t *g_best;
-    int32_t *bad_index;       // set to 1 when a gather id is not owned by this store
+    int32_t *flag;            // bit 0 is set when a gather id is not owned by this store
+    // workspace zeroed here (grid-stride, all blocks) instead of by separate memsets
+    uint32_t *gslot;          // [nq * nslot] residue slots
+    int64_t gslot_words;
+    uint32_t *gbound;         // [nq * nblk] block maxima of the bound pass (or null)
+    int64_t gbound_words;
+    int *ctr;                 // tile / visit / bound-completion counters of every query group
+    int ctr_words;
+    float *cbank;             // non-null: device address of c_qhat -- a single-group pass writes its normalised
+    int cbank_q;              // rows (the first cbank_q queries) straight into the constant bank
 };
 
-__global__ void prep_queries_kernel(const PrepArgs a)
+// A gather id this store does not own yields a DEAD query: its threshold starts at +inf, so no
+// regular song passes the filter, no exact key reaches a list, and finalize emits a row of -1 / 0.
+// The engine reports SR_EINVAL at its next synchronising call (sr_engine.h).
+constexpr uint32_t kOrdDead = 0xFF800000u;  // f2ord(+inf)
+
+__global__ void __launch_bounds__(128) prep_queries_kernel(const PrepArgs a)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= a.nq) return;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
+    {
+        uint4 *g4 = reinterpret_cast<uint4 *>(a.gslot);  // nslot is a multiple of 32 words
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int64_t i = gtid; i < a.gslot_words / 4; i += gthreads) g4[i] = z;
+        for (int64_t i = gtid; i < a.gbound_words; i += gthreads) a.gbound[i] = 0u;
+        for (int64_t i = gtid; i < a.ctr_words; i += gthreads) a.ctr[i] = 0;
+    }
+    const int q = (int)gtid;
+    if (gtid >= a.nq) return;
     float v[kF];
     int32_t ex = -1;
+    bool dead = false;
     if (a.qidx) {
         int64_t local = (int64_t)a.qidx[q] - a.id_base;
         if (local < 0 || local >= a.n) {
-            *a.bad_index = 1;
+            atomicOr(a.flag, 1);
+            dead = true;
             local = 0;
         }
         load_row12(a.raw_store, local, v);
@@ -107,10 +132,12 @@ __global__ void prep_queries_kernel(const PrepArgs a)
     for (int j = 0; j < kF; ++j) {
         // an irregular query (zero / tiny / huge / non-finite norm) carries NaN: every
         // pair passes the filter and is scored exactly
-        a.qhat[(size_t)q * kF + j] = regular ? (float)((double)v[j] * inv) : qnan;
+        const float h = regular ? (float)((double)v[j] * inv) : qnan;
+        a.qhat[(size_t)q * kF + j] = h;
+        if (a.cbank && q < a.cbank_q) a.cbank[(size_t)q * kF + j] = h;
     }
     a.pool_cnt[q] = 0;
-    a.g_best[q] = kOrdNegInf;
+    a.g_best[q] = dead ? kOrdDead : kOrdNegInf;
 }
 
 // ---- threshold bootstrap (stores too small for the bound pass) -----------------------------
@@ -227,8 +254,13 @@ struct FinalArgs {
     const uint64_t *pool;
     const int32_t *pool_cnt;
     int nq, K, slab;     // slab: keys per query in the pool
-    int32_t *out_idx;    // [nq][K]
-    float *out_score;    // [nq][K] or null
+    int stride, col;     // output rows are `stride` wide; this pass fills columns [col, col + K)
+    int32_t *out_idx;    // [nq][stride] or null
+    float *out_score;    // [nq][stride] or null
+    uint64_t *out_keys;  // [nq][stride] packed (score, id) keys, 0 = none (row-shard exchange format) or null
+    uint64_t *ceil_out;  // [nq] or null: the K-th key of this pass (0 when the store is exhausted) -- the next
+                         // pass of a K > kKMax query only admits keys below it
+    int32_t *flag;       // bit 1 is set if a pool slab overflowed (must never happen: sizing bug)
 };
 
 template <int THREADS>
@@ -238,38 +270,72 @@ __global__ void __launch_bounds__(THREADS) finalize_kernel(const FinalArgs a)
     const int q = blockIdx.x;
     if (q >= a.nq) return;
     const uint64_t *slab = a.pool + (size_t)q * a.slab;
-    const int P = a.pool_cnt[q];
+    int P = a.pool_cnt[q];
+    if (P > a.slab) {
+        if (threadIdx.x == 0) atomicOr(a.flag, 2);
+        P = a.slab;
+    }
     int valid = 0;
     if (P > 0) valid = block_select_topk<THREADS>(s_keys, P, a.K, [&](int i) { return slab[i]; });
+    const size_t row = (size_t)q * a.stride + a.col;
     for (int r = threadIdx.x; r < a.K; r += THREADS) {
         const bool ok = r < valid;
         const uint64_t k = ok ? s_keys[r] : 0ull;
-        a.out_idx[(size_t)q * a.K + r] = ok ? (int32_t)key_id(k) : -1;
-        if (a.out_score) a.out_score[(size_t)q * a.K + r] = ok ? key_score(k) : 0.0f;
+        if (a.out_idx) a.out_idx[row + r] = ok ? (int32_t)key_id(k) : -1;
+        if (a.out_score) a.out_score[row + r] = ok ? key_score(k) : 0.0f;
+        if (a.out_keys) a.out_keys[row + r] = k;
     }
+    if (a.ceil_out && threadIdx.x == 0) a.ceil_out[q] = (valid == a.K) ? s_keys[a.K - 1] : 0ull;
 }
 
 // ---- multi-GPU merge: parts x nq x K lists -> one list per query ----
+// The exchange format is the packed key (orderable score << 32 | ~id, 0 = none): one 64-bit word
+// per candidate, so a step needs exactly ONE all-gather; `keys` non-null selects it, else the
+// (idx, score) pair of arrays is read (-1 padded).
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) merge_parts_kernel(const int32_t *idx, const float *score, int parts,
-                                                               int nq, int K, int32_t *out_idx, float *out_score)
+__global__ void __launch_bounds__(THREADS) merge_parts_kernel(const uint64_t *keys, const uint64_t *const *part_keys, const int32_t *idx,
+                                                               const float *score, int parts, int nq, int K, int32_t *out_idx,
+                                                               float *out_score, int stride, int col, uint64_t *ceil_out)
 {
     __shared__ uint64_t s_keys[kSortCap];
     const int q = blockIdx.x;
     if (q >= nq) return;
+    // part_keys: one base pointer per shard ([nq][K] each) -- in the single-process multi-GPU host these are the
+    // shards' own result buffers, read here over NVLink peer access: gather and merge in one kernel
     auto item = [&](int i) -> uint64_t {
         const int p = i / K, r = i - p * K;
+        if (part_keys) return __ldcg(part_keys[p] + (size_t)q * K + r);
         const size_t at = ((size_t)p * nq + q) * K + r;
+        if (keys) return keys[at];
         const int32_t id = idx[at];
         return id < 0 ? 0ull : make_key(score[at], (uint32_t)id);
     };
     const int valid = block_select_topk<THREADS>(s_keys, parts * K, K, item);
+    const size_t row = (size_t)q * stride + col;
     for (int r = threadIdx.x; r < K; r += THREADS) {
         const bool ok = r < valid;
         const uint64_t k = ok ? s_keys[r] : 0ull;
-        out_idx[(size_t)q * K + r] = ok ? (int32_t)key_id(k) : -1;
-        if (out_score) out_score[(size_t)q * K + r] = ok ? key_score(k) : 0.0f;
+        out_idx[row + r] = ok ? (int32_t)key_id(k) : -1;
+        if (out_score) out_score[row + r] = ok ? key_score(k) : 0.0f;
     }
+    if (ceil_out && threadIdx.x == 0) ceil_out[q] = (valid == K) ? s_keys[K - 1] : 0ull;
+}
+
+// rows of global ids for every shard of a single-process multi-GPU store: raw[s] is shard s's raw-row matrix (peer
+// memory), shard s owns ids [s * per, ...): out[i] = row of ids[i], zeros for ids outside [0, n_total)
+__global__ void gather_rows_p2p_kernel(const float *const *raw, int64_t per, int64_t n_total, const int32_t *ids, int count, float *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t id = ids[i];
+    float4 *o = reinterpret_cast<float4 *>(out) + (size_t)i * 3;
+    if (id < 0 || id >= n_total) {
+        o[0] = o[1] = o[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const int64_t s = id / per;
+    const float4 *p = reinterpret_cast<const float4 *>(raw[s]) + (id - s * per) * 3;
+    o[0] = __ldcg(p); o[1] = __ldcg(p + 1); o[2] = __ldcg(p + 2);
 }
 
 // ---- row gather (multi-GPU query exchange) --------------------------------

@@ -26,8 +26,8 @@ thread_local std::string g_create_error;
 // ---- scan kernel shapes --------------------------------------------------------
 typedef cudaError_t (*ScanLaunch)(const ScanArgs &, int grid, size_t smem, cudaStream_t st);
 typedef cudaError_t (*ScanOcc)(int *ctas_per_sm, size_t smem);
-typedef cudaError_t (*BoundLaunch)(const ScanArgs &, int nblk, int n_sample, int stride, uint32_t *gmax, int grid, size_t smem,
-                                   cudaStream_t st);
+typedef cudaError_t (*BoundLaunch)(const ScanArgs &, int nblk, int n_sample, int stride, uint32_t *gmax, int *done_ctr, int grid,
+                                   size_t smem, cudaStream_t st);
 
 template <int S, int T, int M, bool D, bool G, bool Y>
 cudaError_t launch_scan(const ScanArgs &a, int grid, size_t smem, cudaStream_t st)
@@ -48,13 +48,13 @@ cudaError_t occ_scan(int *ctas, size_t smem)
 }
 
 template <int S, int T, int M>
-cudaError_t launch_bound(const ScanArgs &a, int nblk, int n_sample, int stride, uint32_t *gmax, int grid, size_t smem,
+cudaError_t launch_bound(const ScanArgs &a, int nblk, int n_sample, int stride, uint32_t *gmax, int *done_ctr, int grid, size_t smem,
                          cudaStream_t st)
 {
     auto k = bound_kernel<S, T, M>;
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    k<<<grid, T, smem, st>>>(a, nblk, n_sample, stride, gmax);
+    k<<<grid, T, smem, st>>>(a, nblk, n_sample, stride, gmax, done_ctr);
     return cudaGetLastError();
 }
 
@@ -117,17 +117,24 @@ struct sr_engine {
     int trigger_at = 0; // 0: cap / 4
     int hit_cap = 0;   // hit-buffer entries per query in shared memory (0: sized from K)
     int list_ws_opt = 1;    // allow the CTAs' lists in an L2-resident workspace when that keeps the query tile at full size
+    int list_ws_kmax = 72;  // ... for k up to this
+    int small_max = 40;     // batches of at most this many queries take the TMA-staged small-batch shape
     int bound_tiles = 0;    // layout tiles (of S x 256 songs) the bound pass samples (0: 48 for k <= 16, else 128)
     bool profile = false;
 
     // batch workspace (grow-only)
-    DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, tile_ctr, pool_cnt, pool, out_idx, out_score, qin, exin, minmax, list_ws;
+    DevBuf qraw, qn, qhat, excl, gbest, gbound, gslot, ctr, pool_cnt, pool, out, out2, qin, minmax, list_ws, ceil;
     unsigned long long *d_stats = nullptr;  // [16]
     unsigned long long *d_irregular = nullptr;
-    int32_t *d_flag = nullptr;
+    int32_t *d_flag = nullptr;   // bit 0: a query id this store does not own; bit 1: a pool slab overflowed
+    int32_t *h_flag = nullptr;   // pinned mirror
+    float *d_cbank = nullptr;    // device address of the constant bank c_qhat
     void *h_pin = nullptr;
     size_t h_pin_cap = 0;
+    cudaStream_t copy_stream = nullptr;  // all-pairs: result copies overlap the next batch
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     int scan_grid = 0;
+    int last_lists_in_smem = 1;
 
     // counters
     int64_t launches = 0, queries = 0;
@@ -286,14 +293,24 @@ int alloc_store(sr_engine *e, int64_t n, int64_t id_base)
 std::mutex g_bank_mutex;
 cudaEvent_t g_bank_event[64] = {nullptr};
 
-// One internal pass: nq <= e->batch queries, everything on device, stream-ordered.
+// where one internal pass delivers its rows
+struct PassOut {
+    int32_t *idx = nullptr;     // [nq][stride] or null
+    float *score = nullptr;     // [nq][stride] or null
+    uint64_t *keys = nullptr;   // [nq][stride] packed keys or null
+    int stride = 0, col = 0;    // the pass fills columns [col, col + K)
+    const uint64_t *ceil_in = nullptr;  // [nq] only keys below these are admitted (or null)
+    uint64_t *ceil_out = nullptr;       // [nq] receives the K-th key of the pass (or null)
+};
+
+// One internal pass: nq <= e->batch queries, K <= kKMax, everything on device, stream-ordered.
 int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const int32_t *d_excl, int nq, int K,
-             int32_t *d_out_idx, float *d_out_score, cudaStream_t st)
+             const PassOut &out, cudaStream_t st)
 {
     // small batches are HBM-bound: two 256-thread CTAs per SM, song tiles staged through shared
     // memory by TMA one tile ahead; large batches are FP32-bound: one 512-thread CTA, bigger
     // tiles, shared memory spent on 256 queries' lists and hit buffers
-    int vi = e->variant >= 0 ? e->variant : (nq <= 40 ? kAutoSmall : kAutoLarge);
+    int vi = e->variant >= 0 ? e->variant : (nq <= e->small_max ? kAutoSmall : kAutoLarge);
     const Variant *vp = nullptr;
     int TS = 0, n_tiles = 0, groups = 0, gsize = 0, qt_cap = 0, cap = 0;
     bool lists_in_smem = true;
@@ -325,7 +342,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             // tile of half the size costs 6 % of the whole scan; measured: wins up to k ~ 72, beyond
             // that twice as many CTAs per query with long lists of their own cost more)
             for (int in_smem = 1; in_smem >= 0 && !qt_cap; --in_smem) {
-                if (!in_smem && !(e->list_ws_opt && K <= 72 && qtry == qt_max && qtry >= 128 && vp->ctas == 1 && !vp->staged)) break;
+                if (!in_smem && !(e->list_ws_opt && K <= e->list_ws_kmax && qtry == qt_max && qtry >= 128 && vp->ctas == 1 && !vp->staged)) break;
                 for (int ci = 0; ci < 4 && !qt_cap; ++ci) {
                     const int ctry = std::min(1024, (caps[ci] + 31) / 32 * 32);
                     if (ctry > 0 && scan_smem_bytes(qtry, ctry, K, stage_bytes, in_smem != 0) <= smem_budget) {
@@ -342,6 +359,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     const int qt = (gsize + nqt0 - 1) / nqt0;
     const int nqt = (gsize + qt - 1) / qt;
     if (!lists_in_smem && scan_smem_bytes(qt, cap, K, stage_bytes, true) <= (size_t)216 * 1024 / v.ctas) lists_in_smem = true;  // few queries: they fit after all
+    e->last_lists_in_smem = lists_in_smem ? 1 : 0;
     const size_t smem = scan_smem_bytes(qt, cap, K, stage_bytes, lists_in_smem);
     int ctas = 0;
     SR_CUDA(v.occ(&ctas, smem));
@@ -350,22 +368,28 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if (units > 0x7fffffffLL) return fail(e, SR_EINVAL, "store too large for one pass (%lld work units)", (long long)units);
     const int grid = (int)std::min<int64_t>((int64_t)e->sm_count * ctas, units);
     e->scan_grid = grid;
-    int upc_min = 0x7fffffff;  // fewest units per CTA over the groups of this pass => most segments per query tile
-    for (int g0 = 0; g0 < nq; g0 += gsize) {
-        const int64_t gunits = (int64_t)((std::min(gsize, nq - g0) + qt - 1) / qt) * n_tiles;
-        upc_min = (int)std::min<int64_t>(upc_min, std::max<int64_t>(1, gunits / std::min<int64_t>(grid, gunits)));
-    }
-    // (dynamic shapes: a query tile's home CTAs plus the late joiners it admits)
+    // Pool slab of a query = the most CTA segments any of this pass's groups can put on one query tile: static
+    // shapes deal contiguous runs of at least upc units; dynamic shapes have their home CTAs plus the late
+    // joiners a tile admits (a short last group has fewer query tiles, hence more CTAs on each)
     const int steal_max = std::min(grid, 16);
-    const int segs = std::max(scan_segs(n_tiles, upc_min), grid / std::max(1, nqt) + 3 + (v.dynamic ? steal_max : 0));
+    int upc_min = 0x7fffffff, cpq_max = 0;
+    for (int g0 = 0; g0 < nq; g0 += gsize) {
+        const int gnqt = (std::min(gsize, nq - g0) + qt - 1) / qt;
+        const int64_t gunits = (int64_t)gnqt * n_tiles;
+        const int64_t ggrid = std::min<int64_t>(grid, gunits);
+        upc_min = (int)std::min<int64_t>(upc_min, std::max<int64_t>(1, gunits / ggrid));
+        cpq_max = std::max(cpq_max, (int)(ggrid / gnqt));
+    }
+    const int segs = std::max(scan_segs(n_tiles, upc_min), cpq_max + 3 + (v.dynamic ? steal_max : 0));
 
     // threshold bootstrap: the bound pass (filter speed, per query group) when the store has
-    // enough full tiles, else the exact sample
+    // enough full tiles, else the exact sample.  Neither is valid under a ceiling (they bound the
+    // K-th best of ALL songs, a ceiling pass wants the K-th best below the ceiling).
     const int64_t full_tiles = e->n / TS;
     const int nblk = K + 1;                                  // disjoint blocks of sample songs
     // sample tiles: 48 (short lists) or 128 layout tiles on large stores, never more than ~6 % of the store
     const int n_sample = (int)std::min<int64_t>({(int64_t)(e->bound_tiles > 0 ? e->bound_tiles : (K <= 16 ? 48 : 128)) / (v.threads / kLT), std::max<int64_t>(4, full_tiles / 16), full_tiles / 4});
-    const bool use_bound = e->bound && nblk <= kLT / 2 && n_sample >= 4 && (int64_t)n_sample * TS >= 64 * (int64_t)nblk;
+    const bool use_bound = e->bound && !out.ceil_in && nblk <= kLT / 2 && n_sample >= 4 && (int64_t)n_sample * TS >= 64 * (int64_t)nblk;
 
     int rc;
     if ((rc = ensure(e, e->qraw, (size_t)nq * kF * 4))) return rc;
@@ -376,7 +400,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->gbound, (size_t)nq * nblk * 4))) return rc;
     const int nslot = std::max(256, (K + 31) / 32 * 32);  // residue slots per query (global threshold feedback)
     if ((rc = ensure(e, e->gslot, (size_t)nq * nslot * 4))) return rc;
-    if ((rc = ensure(e, e->tile_ctr, (size_t)(nqt + 1) * 8))) return rc;
+    const int ctr_per_group = 2 * nqt + 2;                // tile counters, visit counters, bound-pass completion
+    if ((rc = ensure(e, e->ctr, (size_t)groups * ctr_per_group * 4))) return rc;
     if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
     // settle triggers: a quarter-full buffer starts a settle phase (earlier settles = tighter thresholds = fewer
     // hits to re-run the filter for: 863 -> 474 per query at 10 M songs, 1.7 % of the scan), which takes every buffer
@@ -390,23 +415,35 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->pool, (size_t)nq * slab * 8))) return rc;
     if (!lists_in_smem && (rc = ensure(e, e->list_ws, (size_t)grid * qt * K * 8))) return rc;
 
-    SR_CUDA(cudaMemsetAsync(e->gslot.p, 0, (size_t)nq * nslot * 4, st));
-    if (use_bound) SR_CUDA(cudaMemsetAsync(e->gbound.p, 0, (size_t)nq * nblk * 4, st));
+    // the constant bank is free once the last scan that read it has finished (on whichever stream)
+    std::lock_guard<std::mutex> lock(g_bank_mutex);
+    cudaEvent_t &ev = g_bank_event[e->device & 63];
+    if (!ev) SR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    else SR_CUDA(cudaStreamWaitEvent(st, ev, 0));
     {
+        // one kernel resets the pass's workspace, prepares the queries and -- for a single-group pass --
+        // writes the normalised rows straight into the constant bank
         PrepArgs p;
         p.raw_store = e->d_raw; p.n = e->n; p.id_base = e->id_base;
         p.qidx = d_qidx; p.qrows_in = d_qrows; p.excl_in = d_excl; p.nq = nq;
         p.qraw = (float *)e->qraw.p; p.qn = (float *)e->qn.p; p.qhat = (float *)e->qhat.p;
         p.excl = (int32_t *)e->excl.p; p.pool_cnt = (int32_t *)e->pool_cnt.p;
         p.g_best = (uint32_t *)e->gbest.p;
-        p.bad_index = e->d_flag;
+        p.flag = e->d_flag;
+        p.gslot = (uint32_t *)e->gslot.p; p.gslot_words = (int64_t)nq * nslot;
+        p.gbound = use_bound ? (uint32_t *)e->gbound.p : nullptr; p.gbound_words = use_bound ? (int64_t)nq * nblk : 0;
+        p.ctr = (int *)e->ctr.p; p.ctr_words = groups * ctr_per_group;
+        p.cbank = groups == 1 ? e->d_cbank : nullptr; p.cbank_q = nq;
+        const int64_t zero_words = p.gslot_words / 4 + p.gbound_words + p.ctr_words;
+        const int blocks = (int)std::max<int64_t>((nq + 127) / 128, std::min<int64_t>((int64_t)e->sm_count * 4, (zero_words + 128 * 8 - 1) / (128 * 8)));
         Scope sc(e, st, kPrep);
-        prep_queries_kernel<<<(nq + 127) / 128, 128, 0, st>>>(p);
+        prep_queries_kernel<<<blocks, 128, 0, st>>>(p);
         SR_CUDA(cudaGetLastError());
     }
     // threshold bootstrap: the bound pass (filter speed, per query group, below) when the store
     // has enough full tiles, else / additionally the exact sample
     int m = e->sample;
+    if (out.ceil_in) m = 0;
     if (m < 0 && use_bound) m = 0;
     if (m < 0) m = std::min(kSortCap, std::max(1024, 2 * pow2_floor((int64_t)K * 32 - 1)));
     if (m > 0) {
@@ -421,7 +458,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             SR_CUDA(cudaGetLastError());
         }
     }
-    for (int g0 = 0; g0 < nq; g0 += gsize) {
+    int gi = 0;
+    for (int g0 = 0; g0 < nq; g0 += gsize, ++gi) {
         const int gq = std::min(gsize, nq - g0);
         ScanArgs a;
         a.hat = e->d_hat; a.raw = e->d_raw; a.nf = e->d_nf; a.n = e->n; a.id_base = e->id_base;
@@ -433,18 +471,18 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.trigger_at = trigger_at_eff;
         a.gslot = (uint32_t *)e->gslot.p + (size_t)g0 * nslot;
         a.nslot = nslot;
+        a.ceil = out.ceil_in ? out.ceil_in + g0 : nullptr;
         a.pool = (uint64_t *)e->pool.p + (size_t)g0 * slab; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
         a.segs = segs; a.slab = slab;
         a.g_best = (uint32_t *)e->gbest.p + g0;
         a.list_ws = lists_in_smem ? nullptr : (uint64_t *)e->list_ws.p;
         a.stats = e->d_stats;
         const int gnqt = (gq + qt - 1) / qt;
-        std::lock_guard<std::mutex> lock(g_bank_mutex);
-        cudaEvent_t &ev = g_bank_event[e->device & 63];
-        if (!ev) SR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        else SR_CUDA(cudaStreamWaitEvent(st, ev, 0));
-        SR_CUDA(cudaMemcpyToSymbolAsync(c_qhat, (const float *)e->qhat.p + (size_t)g0 * kF, (size_t)gq * kF * 4, 0,
-                                        cudaMemcpyDeviceToDevice, st));
+        int *gctr = (int *)e->ctr.p + (size_t)gi * ctr_per_group;
+        if (groups > 1) {  // (stream order keeps the upload behind the previous group's scan)
+            SR_CUDA(cudaMemcpyToSymbolAsync(c_qhat, (const float *)e->qhat.p + (size_t)g0 * kF, (size_t)gq * kF * 4, 0,
+                                            cudaMemcpyDeviceToDevice, st));
+        }
         if (use_bound) {
             // its own (finer) query tiles: the block maxima of a tile live in shared memory
             ScanArgs b = a;
@@ -452,13 +490,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             const int bnqt = (gq + b.qt - 1) / b.qt;
             const int bgrid = (int)std::min<int64_t>((int64_t)e->sm_count * v.ctas, (int64_t)bnqt * n_sample);
             uint32_t *gmax = (uint32_t *)e->gbound.p + (size_t)g0 * nblk;
-            {
-                Scope sc(e, st, kBound);
-                SR_CUDA(v.bound(b, nblk, n_sample, (int)(full_tiles / n_sample), gmax, bgrid, (size_t)b.qt * nblk * 4, st));
-            }
-            bound_finish_kernel<<<(gq + 127) / 128, 128, 0, st>>>(gmax, nblk, a.g_best, gq);
-            SR_CUDA(cudaGetLastError());
-            ++e->launches;
+            Scope sc(e, st, kBound);
+            SR_CUDA(v.bound(b, nblk, n_sample, (int)(full_tiles / n_sample), gmax, gctr + 2 * nqt, bgrid, (size_t)b.qt * nblk * 4, st));
         }
         {
             a.n_tiles = n_tiles;
@@ -468,15 +501,12 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             a.upc = (int)(gunits / ggrid);
             a.extra = (int)(gunits % ggrid);
             a.cpq = 0;
-            a.tile_ctr = (int *)e->tile_ctr.p;
-            a.visit_ctr = a.tile_ctr + gnqt;
+            a.tile_ctr = gctr;
+            a.visit_ctr = gctr + nqt;
             a.steal_max = steal_max;
             const Variant *vl = &v;
             if (v.dynamic && gnqt > ggrid) vl = &kVariants[kStaticLarge];  // more query tiles than CTAs: static runs (same S, threads, smem)
-            if (vl->dynamic) {
-                a.cpq = ggrid / gnqt;
-                SR_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, (size_t)gnqt * 8, st));
-            }
+            if (vl->dynamic) a.cpq = ggrid / gnqt;
             Scope sc(e, st, kScan);
             SR_CUDA(vl->launch(a, ggrid, smem, st));
         }
@@ -485,7 +515,10 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     {
         FinalArgs f;
         f.pool = (uint64_t *)e->pool.p; f.pool_cnt = (int32_t *)e->pool_cnt.p;
-        f.nq = nq; f.K = K; f.slab = slab; f.out_idx = d_out_idx; f.out_score = d_out_score;
+        f.nq = nq; f.K = K; f.slab = slab;
+        f.stride = out.stride > 0 ? out.stride : K; f.col = out.col;
+        f.out_idx = out.idx; f.out_score = out.score; f.out_keys = out.keys;
+        f.ceil_out = out.ceil_out; f.flag = e->d_flag;
         Scope sc(e, st, kFinalize);
         finalize_kernel<256><<<nq, 256, 0, st>>>(f);
         SR_CUDA(cudaGetLastError());
@@ -507,21 +540,48 @@ int check_query_args(sr_engine *e, const void *q, int nq, int k, const void *out
     if (!e->d_raw) return fail(e, SR_ESTATE, "no store loaded: call sr_engine_load_features first");
     if (!q || !out_idx) return fail(e, SR_EINVAL, "null query or output pointer");
     if (nq <= 0) return fail(e, SR_EINVAL, "nq must be positive (got %d)", nq);
-    if (k <= 0 || k > kKMax) return fail(e, SR_EINVAL, "k must be in [1, %d] (got %d)", kKMax, k);
+    if (k <= 0) return fail(e, SR_EINVAL, "k must be positive (got %d)", k);
     return SR_OK;
 }
 
+// A batch of any size and any k: internal passes of <= e->batch queries; a k beyond kKMax is served kKMax
+// results at a time, each pass admitting only keys below the last key of the pass before (the ceiling), so the
+// caller sees min(k, songs - 1) results per query like the reference (Recommender.cu:300-315).
 int run_device(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const int32_t *d_excl, int nq, int k,
-               int32_t *d_out_idx, float *d_out_score, cudaStream_t st)
+               int32_t *d_out_idx, float *d_out_score, uint64_t *d_out_keys, const uint64_t *d_ceil, cudaStream_t st)
 {
+    const int chunks = (k + kKMax - 1) / kKMax;
     for (int done = 0; done < nq; done += e->batch) {
         const int cur = std::min(e->batch, nq - done);
-        int rc = run_pass(e, d_qidx ? d_qidx + done : nullptr, d_qrows ? d_qrows + (size_t)done * kF : nullptr,
-                          d_excl ? d_excl + done : nullptr, cur, k, d_out_idx + (size_t)done * k,
-                          d_out_score ? d_out_score + (size_t)done * k : nullptr, st);
-        if (rc) return rc;
+        int rc;
+        if (chunks > 1 && (rc = ensure(e, e->ceil, (size_t)cur * 8))) return rc;
+        for (int c = 0; c < chunks; ++c) {
+            PassOut o;
+            o.stride = k; o.col = c * kKMax;
+            o.idx = d_out_idx ? d_out_idx + (size_t)done * k : nullptr;
+            o.score = d_out_score ? d_out_score + (size_t)done * k : nullptr;
+            o.keys = d_out_keys ? d_out_keys + (size_t)done * k : nullptr;
+            o.ceil_in = c > 0 ? (const uint64_t *)e->ceil.p : (d_ceil ? d_ceil + done : nullptr);
+            o.ceil_out = c + 1 < chunks ? (uint64_t *)e->ceil.p : nullptr;
+            rc = run_pass(e, d_qidx ? d_qidx + done : nullptr, d_qrows ? d_qrows + (size_t)done * kF : nullptr,
+                          d_excl ? d_excl + done : nullptr, cur, std::min(kKMax, k - c * kKMax), o, st);
+            if (rc) return rc;
+        }
     }
     return SR_OK;
+}
+
+// the sticky device flag, read at a synchronising call (clears it)
+int check_flag(sr_engine *e, cudaStream_t st)
+{
+    SR_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, 4, cudaMemcpyDeviceToHost, st));
+    SR_CUDA(cudaStreamSynchronize(st));
+    const int f = *e->h_flag;
+    if (!f) return SR_OK;
+    SR_CUDA(cudaMemsetAsync(e->d_flag, 0, 4, st));
+    if (f & 2) return fail(e, SR_ECUDA, "internal error: a result pool overflowed (results of the last batch are incomplete)");
+    return fail(e, SR_EINVAL, "a query id is not a song of this store [%d, %lld): its result row is -1",
+                e->id_base, (long long)(e->id_base + e->n));
 }
 
 // host-buffer front end shared by query_by_index / query_by_vector
@@ -534,24 +594,20 @@ int run_host(sr_engine *e, const int32_t *qidx, const float *qrows, const int32_
     const size_t out_s = out_score ? (size_t)nq * k * 4 : 0;
     int rc;
     if ((rc = ensure_pinned(e, in_q + in_x + out_i + out_s))) return rc;
-    if ((rc = ensure(e, e->qin, in_q))) return rc;
-    if (in_x && (rc = ensure(e, e->exin, in_x))) return rc;
-    if ((rc = ensure(e, e->out_idx, out_i))) return rc;
-    if (out_s && (rc = ensure(e, e->out_score, out_s))) return rc;
+    if ((rc = ensure(e, e->qin, in_q + in_x))) return rc;
+    if ((rc = ensure(e, e->out, out_i + out_s))) return rc;
     char *pin = (char *)e->h_pin;
     memcpy(pin, qidx ? (const void *)qidx : (const void *)qrows, in_q);
     if (in_x) memcpy(pin + in_q, exclude, in_x);
-    SR_CUDA(cudaMemcpyAsync(e->qin.p, pin, in_q, cudaMemcpyHostToDevice, e->stream));
-    if (in_x) SR_CUDA(cudaMemcpyAsync(e->exin.p, pin + in_q, in_x, cudaMemcpyHostToDevice, e->stream));
-    SR_CUDA(cudaMemsetAsync(e->d_flag, 0, 4, e->stream));
-    rc = run_device(e, qidx ? (int32_t *)e->qin.p : nullptr, qidx ? nullptr : (float *)e->qin.p,
-                    in_x ? (int32_t *)e->exin.p : nullptr, nq, k, (int32_t *)e->out_idx.p,
-                    out_s ? (float *)e->out_score.p : nullptr, e->stream);
+    SR_CUDA(cudaMemcpyAsync(e->qin.p, pin, in_q + in_x, cudaMemcpyHostToDevice, e->stream));  // one copy in ...
+    char *d_in = (char *)e->qin.p, *d_out = (char *)e->out.p;
+    rc = run_device(e, qidx ? (int32_t *)d_in : nullptr, qidx ? nullptr : (float *)d_in,
+                    in_x ? (int32_t *)(d_in + in_q) : nullptr, nq, k, (int32_t *)d_out,
+                    out_s ? (float *)(d_out + out_i) : nullptr, nullptr, nullptr, e->stream);
     if (rc) return rc;
     char *pout = pin + in_q + in_x;
-    SR_CUDA(cudaMemcpyAsync(pout, e->out_idx.p, out_i, cudaMemcpyDeviceToHost, e->stream));
-    if (out_s) SR_CUDA(cudaMemcpyAsync(pout + out_i, e->out_score.p, out_s, cudaMemcpyDeviceToHost, e->stream));
-    SR_CUDA(cudaStreamSynchronize(e->stream));
+    SR_CUDA(cudaMemcpyAsync(pout, d_out, out_i + out_s, cudaMemcpyDeviceToHost, e->stream));  // ... one copy out
+    if ((rc = check_flag(e, e->stream))) return rc;
     memcpy(out_idx, pout, out_i);
     if (out_s) memcpy(out_score, pout + out_i, out_s);
     return SR_OK;
@@ -593,6 +649,13 @@ int sr_engine_create(sr_engine **out, int device)
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (err = cudaEventCreateWithFlags(&e->ev_done[0], cudaEventDisableTiming)) != cudaSuccess ||
+        (err = cudaEventCreateWithFlags(&e->ev_done[1], cudaEventDisableTiming)) != cudaSuccess ||
+        (err = cudaEventCreateWithFlags(&e->ev_copied[0], cudaEventDisableTiming)) != cudaSuccess ||
+        (err = cudaEventCreateWithFlags(&e->ev_copied[1], cudaEventDisableTiming)) != cudaSuccess ||
+        (err = cudaGetSymbolAddress((void **)&e->d_cbank, c_qhat)) != cudaSuccess ||
+        (err = cudaMallocHost((void **)&e->h_flag, 4)) != cudaSuccess ||
         (err = cudaMalloc(&e->d_stats, 16 * 8)) != cudaSuccess || (err = cudaMalloc(&e->d_irregular, 8)) != cudaSuccess ||
         (err = cudaMalloc(&e->d_flag, 4)) != cudaSuccess || (err = cudaMemset(e->d_stats, 0, 128)) != cudaSuccess ||
         (err = cudaMemset(e->d_flag, 0, 4)) != cudaSuccess) {
@@ -610,8 +673,9 @@ void sr_engine_destroy(sr_engine *e)
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto &t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->tile_ctr, &e->pool_cnt, &e->pool, &e->minmax, &e->list_ws,
-                      &e->out_idx, &e->out_score, &e->qin, &e->exin};
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->ctr, &e->pool_cnt, &e->pool, &e->minmax, &e->list_ws,
+                      &e->out, &e->out2, &e->qin, &e->ceil};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->d_raw) cudaFree(e->d_raw);
@@ -621,6 +685,12 @@ void sr_engine_destroy(sr_engine *e)
     if (e->d_irregular) cudaFree(e->d_irregular);
     if (e->d_flag) cudaFree(e->d_flag);
     if (e->h_pin) cudaFreeHost(e->h_pin);
+    if (e->h_flag) cudaFreeHost(e->h_flag);
+    for (int i = 0; i < 2; ++i) {
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+        if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -681,7 +751,7 @@ int sr_engine_query_by_index_dev(sr_engine *e, const int32_t *d_qidx, int nq, in
     if (rc) return rc;
     SR_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = pick_stream(e, stream);
-    return run_device(e, d_qidx, nullptr, nullptr, nq, k, d_out_idx, d_out_score, st);
+    return run_device(e, d_qidx, nullptr, nullptr, nq, k, d_out_idx, d_out_score, nullptr, nullptr, st);
 }
 
 int sr_engine_query_by_vector_dev(sr_engine *e, const float *d_qrows, const int32_t *d_exclude, int nq, int k,
@@ -691,21 +761,47 @@ int sr_engine_query_by_vector_dev(sr_engine *e, const float *d_qrows, const int3
     if (rc) return rc;
     SR_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = pick_stream(e, stream);
-    return run_device(e, nullptr, d_qrows, d_exclude, nq, k, d_out_idx, d_out_score, st);
+    return run_device(e, nullptr, d_qrows, d_exclude, nq, k, d_out_idx, d_out_score, nullptr, nullptr, st);
 }
+
+int sr_engine_query_keys_by_vector_dev(sr_engine *e, const float *d_qrows, const int32_t *d_exclude, int nq, int k,
+                                       const uint64_t *d_ceil, uint64_t *d_out_keys, void *stream)
+{
+    int rc = check_query_args(e, d_qrows, nq, k, d_out_keys);
+    if (rc) return rc;
+    if (k > kKMax) return fail(e, SR_EINVAL, "query_keys: k must be in [1, %d] (got %d); longer lists go %d at a time under a ceiling", kKMax, k, kKMax);
+    SR_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = pick_stream(e, stream);
+    return run_device(e, nullptr, d_qrows, d_exclude, nq, k, nullptr, nullptr, d_out_keys, d_ceil, st);
+}
+
+namespace {
+int merge_common(sr_engine *e, const uint64_t *d_keys, const uint64_t *const *d_part_keys, const int32_t *d_idx, const float *d_score,
+                 int parts, int nq, int k, int32_t *d_out_idx, float *d_out_score, int stride, int col, uint64_t *d_ceil_out, void *stream)
+{
+    if (!e) return SR_EINVAL;
+    if ((!d_keys && !d_part_keys && !(d_idx && d_score)) || !d_out_idx) return fail(e, SR_EINVAL, "merge: null pointer");
+    if (parts <= 0 || nq <= 0 || k <= 0 || k > kKMax) return fail(e, SR_EINVAL, "merge: bad parts/nq/k (k must be in [1, %d])", kKMax);
+    if (stride < col + k) return fail(e, SR_EINVAL, "merge: output window [%d, %d) exceeds the row stride %d", col, col + k, stride);
+    SR_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = pick_stream(e, stream);
+    Scope sc(e, st, kMerge);
+    merge_parts_kernel<256><<<nq, 256, 0, st>>>(d_keys, d_part_keys, d_idx, d_score, parts, nq, k, d_out_idx, d_out_score, stride, col, d_ceil_out);
+    SR_CUDA(cudaGetLastError());
+    return SR_OK;
+}
+}  // namespace
 
 int sr_engine_merge_topk_dev(sr_engine *e, const int32_t *d_idx, const float *d_score, int parts, int nq, int k,
                              int32_t *d_out_idx, float *d_out_score, void *stream)
 {
-    if (!e) return SR_EINVAL;
-    if (!d_idx || !d_score || !d_out_idx) return fail(e, SR_EINVAL, "merge: null pointer");
-    if (parts <= 0 || nq <= 0 || k <= 0 || k > kKMax) return fail(e, SR_EINVAL, "merge: bad parts/nq/k");
-    SR_CUDA(cudaSetDevice(e->device));
-    cudaStream_t st = pick_stream(e, stream);
-    Scope sc(e, st, kMerge);
-    merge_parts_kernel<256><<<nq, 256, 0, st>>>(d_idx, d_score, parts, nq, k, d_out_idx, d_out_score);
-    SR_CUDA(cudaGetLastError());
-    return SR_OK;
+    return merge_common(e, nullptr, nullptr, d_idx, d_score, parts, nq, k, d_out_idx, d_out_score, k, 0, nullptr, stream);
+}
+
+int sr_engine_merge_keys_dev(sr_engine *e, const uint64_t *d_keys, int parts, int nq, int k, int32_t *d_out_idx,
+                             float *d_out_score, int stride, int col, uint64_t *d_ceil_out, void *stream)
+{
+    return merge_common(e, d_keys, nullptr, nullptr, nullptr, parts, nq, k, d_out_idx, d_out_score, stride > 0 ? stride : k, col, d_ceil_out, stream);
 }
 
 int sr_engine_gather_rows_dev(sr_engine *e, const int32_t *d_ids, int count, float *d_out, void *stream)
@@ -800,33 +896,54 @@ int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k, in
     if (!e) return SR_EINVAL;
     if (!e->d_raw) return fail(e, SR_ESTATE, "no store loaded: call sr_engine_load_features first");
     if (!out_idx) return fail(e, SR_EINVAL, "all_pairs: null output");
-    if (k <= 0 || k > kKMax) return fail(e, SR_EINVAL, "k must be in [1, %d] (got %d)", kKMax, k);
+    if (k <= 0) return fail(e, SR_EINVAL, "k must be positive (got %d)", k);
     if (q_lo < e->id_base || q_hi > e->id_base + e->n || q_lo >= q_hi)
         return fail(e, SR_EINVAL, "all_pairs: [%lld, %lld) is not inside this store", (long long)q_lo, (long long)q_hi);
     SR_CUDA(cudaSetDevice(e->device));
-    const int B = e->batch;
+    // Batches of e->batch queries; the results of batch b travel to the host (copy stream, pinned halves) while
+    // batch b + 1 is being scored, and are unpacked into the caller's table while batch b + 2 is enqueued.
+    const int B = (int)std::min<int64_t>(e->batch, q_hi - q_lo);
+    const size_t half = (size_t)B * k * (out_score ? 8 : 4);
     int rc;
     if ((rc = ensure(e, e->qin, (size_t)B * 4))) return rc;
-    if ((rc = ensure(e, e->out_idx, (size_t)B * k * 4))) return rc;
-    if (out_score && (rc = ensure(e, e->out_score, (size_t)B * k * 4))) return rc;
-    if ((rc = ensure_pinned(e, (size_t)B * k * 8))) return rc;
-    for (int64_t lo = q_lo; lo < q_hi; lo += B) {
+    if ((rc = ensure(e, e->out, half))) return rc;
+    if ((rc = ensure(e, e->out2, half))) return rc;
+    if ((rc = ensure_pinned(e, 2 * half))) return rc;
+    char *pin = (char *)e->h_pin;
+    struct Batch { int64_t lo; int cur; } inflight[2] = {{0, 0}, {0, 0}};
+    auto unpack = [&](int sl) {
+        const Batch &b = inflight[sl];
+        const size_t bytes = (size_t)b.cur * k * 4;
+        memcpy(out_idx + (size_t)(b.lo - q_lo) * k, pin + sl * half, bytes);
+        if (out_score) memcpy(out_score + (size_t)(b.lo - q_lo) * k, pin + sl * half + bytes, bytes);
+    };
+    int nb = 0;
+    for (int64_t lo = q_lo; lo < q_hi; lo += B, ++nb) {
+        const int sl = nb & 1;
         const int cur = (int)std::min<int64_t>(B, q_hi - lo);
+        char *d_out = (char *)(sl ? e->out2.p : e->out.p);
+        if (nb >= 2) {  // slot reuse: batch nb - 2 must have left the device buffer and the pinned half
+            SR_CUDA(cudaEventSynchronize(e->ev_copied[sl]));
+            unpack(sl);
+        }
         iota_kernel<<<(cur + 255) / 256, 256, 0, e->stream>>>((int32_t *)e->qin.p, (int32_t)lo, cur);
         SR_CUDA(cudaGetLastError());
         ++e->launches;
-        rc = run_pass(e, (int32_t *)e->qin.p, nullptr, nullptr, cur, k, (int32_t *)e->out_idx.p,
-                      out_score ? (float *)e->out_score.p : nullptr, e->stream);
-        if (rc) return rc;
-        char *pin = (char *)e->h_pin;
         const size_t bytes = (size_t)cur * k * 4;
-        SR_CUDA(cudaMemcpyAsync(pin, e->out_idx.p, bytes, cudaMemcpyDeviceToHost, e->stream));
-        if (out_score) SR_CUDA(cudaMemcpyAsync(pin + bytes, e->out_score.p, bytes, cudaMemcpyDeviceToHost, e->stream));
-        SR_CUDA(cudaStreamSynchronize(e->stream));
-        memcpy(out_idx + (size_t)(lo - q_lo) * k, pin, bytes);
-        if (out_score) memcpy(out_score + (size_t)(lo - q_lo) * k, pin + bytes, bytes);
+        rc = run_device(e, (int32_t *)e->qin.p, nullptr, nullptr, cur, k, (int32_t *)d_out,
+                        out_score ? (float *)(d_out + bytes) : nullptr, nullptr, nullptr, e->stream);
+        if (rc) return rc;
+        SR_CUDA(cudaEventRecord(e->ev_done[sl], e->stream));
+        SR_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_done[sl], 0));
+        SR_CUDA(cudaMemcpyAsync(pin + sl * half, d_out, bytes * (out_score ? 2 : 1), cudaMemcpyDeviceToHost, e->copy_stream));
+        SR_CUDA(cudaEventRecord(e->ev_copied[sl], e->copy_stream));
+        inflight[sl] = {lo, cur};
     }
-    return SR_OK;
+    for (int i = std::max(0, nb - 2); i < nb; ++i) {
+        SR_CUDA(cudaEventSynchronize(e->ev_copied[i & 1]));
+        unpack(i & 1);
+    }
+    return check_flag(e, e->stream);
 }
 
 int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
@@ -861,6 +978,12 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
         e->bound = value != 0;
     } else if (!strcmp(key, "list_ws")) {
         e->list_ws_opt = value != 0;
+    } else if (!strcmp(key, "list_ws_kmax")) {
+        if (value < 0 || value > kKMax) return fail(e, SR_EINVAL, "list_ws_kmax must be in [0, %d]", kKMax);
+        e->list_ws_kmax = (int)value;
+    } else if (!strcmp(key, "small_max")) {
+        if (value < 0 || value > kConstQueries) return fail(e, SR_EINVAL, "small_max must be in [0, %d]", kConstQueries);
+        e->small_max = (int)value;
     } else if (!strcmp(key, "bound_tiles")) {
         if (value != 0 && (value < 8 || value > 1024)) return fail(e, SR_EINVAL, "bound_tiles must be 0 (auto) or in [8, 1024]");
         e->bound_tiles = (int)value;
@@ -908,6 +1031,13 @@ int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value)
     else if (!strcmp(key, "device_bytes")) *value = e->device_bytes;
     else if (!strcmp(key, "variant")) *value = e->last_variant;
     else if (!strcmp(key, "qt")) *value = e->qt_opt;
+    else if (!strcmp(key, "lists_in_smem")) *value = e->last_lists_in_smem;
+    else if (!strcmp(key, "bad_index")) {  // reads (and clears) the sticky flag the device-pointer calls leave behind
+        SR_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, 4, cudaMemcpyDeviceToHost, e->stream));
+        SR_CUDA(cudaStreamSynchronize(e->stream));
+        *value = *e->h_flag;
+        if (*e->h_flag) SR_CUDA(cudaMemsetAsync(e->d_flag, 0, 4, e->stream));
+    }
     else return fail(e, SR_EINVAL, "unknown stat '%s'", key);
     return SR_OK;
 }
@@ -969,13 +1099,15 @@ int sr_engine_selftest_div(sr_engine *e, const float *a, const float *b, int n, 
     SR_CUDA(cudaSetDevice(e->device));
     float *d = nullptr;
     SR_CUDA(cudaMalloc(&d, (size_t)n * 12));
-    SR_CUDA(cudaMemcpy(d, a, (size_t)n * 4, cudaMemcpyHostToDevice));
-    SR_CUDA(cudaMemcpy(d + n, b, (size_t)n * 4, cudaMemcpyHostToDevice));
-    div_selftest_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(d, d + n, d + 2 * (size_t)n, n);
-    SR_CUDA(cudaGetLastError());
-    SR_CUDA(cudaStreamSynchronize(e->stream));
-    SR_CUDA(cudaMemcpy(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    cudaError_t err;
+    if ((err = cudaMemcpy(d, a, (size_t)n * 4, cudaMemcpyHostToDevice)) == cudaSuccess &&
+        (err = cudaMemcpy(d + n, b, (size_t)n * 4, cudaMemcpyHostToDevice)) == cudaSuccess) {
+        div_selftest_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(d, d + n, d + 2 * (size_t)n, n);
+        if ((err = cudaGetLastError()) == cudaSuccess && (err = cudaStreamSynchronize(e->stream)) == cudaSuccess)
+            err = cudaMemcpy(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    }
     cudaFree(d);
+    if (err != cudaSuccess) return fail(e, SR_ECUDA, "selftest_div: %s", cudaGetErrorString(err));
     return SR_OK;
 }
 
@@ -983,8 +1115,9 @@ int sr_engine_synchronize(sr_engine *e)
 {
     if (!e) return SR_EINVAL;
     SR_CUDA(cudaSetDevice(e->device));
-    SR_CUDA(cudaStreamSynchronize(e->stream));
-    return SR_OK;
+    return check_flag(e, e->stream);
 }
 
 }  // extern "C"
+
+#include "sr_sharded.cuh"

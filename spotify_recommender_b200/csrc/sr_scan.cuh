@@ -85,6 +85,8 @@ struct ScanArgs {
     uint32_t *gslot;         // [nq][nslot] lock-free global feedback: slot (id mod nslot) holds the best exact
                              // score (orderable) any CTA has found among the songs with that residue
     int nslot;               // >= K, multiple of 32
+    const uint64_t *ceil;    // null, or [nq] per-query ceiling keys: only keys BELOW the ceiling are admitted (pass p > 0 of a
+                             // K > kKMax query continues below the last key of pass p - 1); offset like the other per-query arrays
     unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] refilters; [5..12] cycle counters (-DSR_SCAN_TIMING)
 };
 
@@ -299,6 +301,7 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
     // only keys above the current threshold can enter (they are compared again inside the merge)
     const uint32_t best_before = c.best[ql];
     const uint64_t floor_key = (uint64_t)best_before << 32;
+    const uint64_t ceil_key = a.ceil ? __ldg(a.ceil + c.qid[ql]) : ~0ull;
     uint64_t kth = 0ull;
     for (int base = 0; base < cnt; base += 128) {
         uint64_t key[4];
@@ -306,7 +309,7 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
         for (int r = 0; r < 4; ++r) {
             const int i = base + r * 32 + lane;
             key[r] = (i < cnt) ? exact_key(a, (int64_t)hit[i] - a.id_base, q, qn, ex) : 0ull;
-            if (key[r] < floor_key) key[r] = 0ull;
+            if (key[r] < floor_key || key[r] >= ceil_key) key[r] = 0ull;
             if (key[r]) atomicMax(a.gslot + (size_t)c.qid[ql] * a.nslot + key_id(key[r]) % (uint32_t)a.nslot, (uint32_t)(key[r] >> 32));
         }
         kth = list_merge4(a, c, ql, key);
@@ -368,7 +371,7 @@ __device__ __forceinline__ void warp_settle(const ScanArgs &a, const QueryCtx &c
                 for (int r = 0; r < 4; ++r) {
                     const int64_t row = base + r * 32 + lane;
                     key[r] = (row < tile_hi) ? exact_key(a, row, q, qn, ex) : 0ull;
-                    if (key[r] < floor_key) key[r] = 0ull;
+                    if (key[r] < floor_key || key[r] >= ceil_key) key[r] = 0ull;
                     if (key[r]) atomicMax(a.gslot + (size_t)c.qid[ql] * a.nslot + key_id(key[r]) % (uint32_t)a.nslot, (uint32_t)(key[r] >> 32));
                 }
                 kth = list_merge4(a, c, ql, key);
@@ -803,8 +806,11 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     for (int j = 0; j < kF; ++j) q[j] = c.qraw[ql * kF + j];
                     const uint64_t key = exact_key(a, (int64_t)c.hit[(size_t)ql * a.cap + (idx - o_own)] - a.id_base, q, c.qn[ql], c.excl[ql]);
                     const uint64_t floor_key = (uint64_t)max(c.best[ql], __ldcg(a.g_best + c.qid[ql])) << 32;
-                    if (key != 0ull && key >= floor_key)
-                        a.pool[(size_t)(q0 + ql) * a.slab + atomicAdd(a.pool_cnt + q0 + ql, 1)] = key;
+                    const uint64_t ceil_key = a.ceil ? __ldg(a.ceil + c.qid[ql]) : ~0ull;
+                    if (key != 0ull && key >= floor_key && key < ceil_key) {
+                        const int at = atomicAdd(a.pool_cnt + q0 + ql, 1);  // (finalize reports a count beyond the slab)
+                        if (at < a.slab) a.pool[(size_t)(q0 + ql) * a.slab + at] = key;
+                    }
                 }
             }
             if (my_cnt) c.cnt[ql_mine] = 0;
@@ -831,7 +837,8 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 int base = 0;
                 if (lane == 0) base = atomicAdd(a.pool_cnt + q0 + ql, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (keep) slab[base + __popc(m & ((1u << lane) - 1u))] = k;
+                const int at = base + __popc(m & ((1u << lane) - 1u));
+                if (keep && at < a.slab) slab[at] = k;
             }
         }
         __syncthreads();
@@ -888,7 +895,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 // Unit u = (query tile, sample tile); each CTA takes whole units.
 template <int S, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) bound_kernel(const ScanArgs a, int nblk, int n_sample, int stride,
-                                                              uint32_t *gmax)
+                                                              uint32_t *gmax, int *done_ctr)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *s_max = reinterpret_cast<uint32_t *>(smem_raw);  // [qt][nblk] orderable block maxima of this unit
@@ -931,24 +938,26 @@ __global__ void __launch_bounds__(THREADS, MINB) bound_kernel(const ScanArgs a, 
             if (s_max[i]) atomicMax(gmax + (size_t)q0 * nblk + i, s_max[i]);
         __syncthreads();
     }
-}
-
-// K+1 disjoint blocks each hold a song whose filter score is >= the block maximum, at most
-// one of them the query song itself: the exact K-th best is >= min(block maxima) - kBoundSlack.
-// Folded into g_best here rather than in the scan's prologue (ptxas drops the scan's
-// uniform-register operands when this arithmetic is inlined there).
-__global__ void bound_finish_kernel(const uint32_t *gmax, int nblk, uint32_t *g_best, int nq)
-{
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    uint32_t mn = 0xFFFFFFFFu;
-    for (int r = 0; r < nblk; ++r) {
-        const uint32_t v = gmax[(size_t)q * nblk + r];
-        mn = v < mn ? v : mn;
+    // The CTA that finishes last folds the block maxima into the starting thresholds: K+1 disjoint blocks each
+    // hold a song whose filter score is >= the block maximum, at most one of them the query song itself, so the
+    // exact K-th best is >= min(block maxima) - kBoundSlack.
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(done_ctr, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int q = tid; q < a.nq; q += THREADS) {
+        uint32_t mn = 0xFFFFFFFFu;
+        for (int r = 0; r < nblk; ++r) {
+            const uint32_t v = __ldcg(gmax + (size_t)q * nblk + r);
+            mn = v < mn ? v : mn;
+        }
+        if (mn == 0u || mn == 0xFFFFFFFFu) continue;  // an empty block: no bound
+        const uint32_t o = f2ord(ord2f(mn) - kBoundSlack);
+        if (o > a.g_best[q]) a.g_best[q] = o;
     }
-    if (mn == 0u || mn == 0xFFFFFFFFu) return;  // an empty block: no bound
-    const uint32_t o = f2ord(ord2f(mn) - kBoundSlack);
-    if (o > g_best[q]) g_best[q] = o;
 }
 
 }  // namespace sr

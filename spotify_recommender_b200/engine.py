@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-ENGINE_SO = os.path.join(PKG, "libsr_engine.so")
+ENGINE_SO = os.environ.get("SR_ENGINE_SO") or os.path.join(PKG, "libsr_engine.so")  # (the override: development builds)
 FEATURE_COUNT = 12  # reference Song.h:12
 
 SR_OK, SR_EINVAL, SR_ENODEVICE, SR_ECUDA, SR_ENOMEM, SR_ESTATE = range(6)
@@ -25,6 +25,9 @@ EXPORTS = [
     "sr_engine_merge_topk_dev", "sr_engine_gather_rows_dev", "sr_engine_all_pairs_topk", "sr_engine_set_option", "sr_engine_get_stat",
     "sr_engine_get_timing", "sr_engine_variant_name", "sr_engine_measure_fp32", "sr_engine_selftest_div",
     "sr_engine_synchronize", "sr_engine_normalize_features", "sr_engine_normalize_features_dev", "sr_genre_ids",
+    "sr_engine_query_keys_by_vector_dev", "sr_engine_merge_keys_dev",
+    "sr_sharded_create", "sr_sharded_destroy", "sr_sharded_last_error", "sr_sharded_load_features", "sr_sharded_song_count",
+    "sr_sharded_shard_count", "sr_sharded_engine", "sr_sharded_query_by_index", "sr_sharded_all_pairs_topk",
 ]
 
 
@@ -75,6 +78,21 @@ def load_library() -> C.CDLL:
     L.sr_engine_normalize_features.argtypes = [vp, vp, vp, i64, i32, vp, vp]
     L.sr_engine_normalize_features_dev.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
     L.sr_genre_ids.argtypes = [C.POINTER(C.c_char_p), i64, i32, vp, C.POINTER(C.c_int32)]
+    L.sr_engine_query_keys_by_vector_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.sr_engine_merge_keys_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]
+    L.sr_sharded_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i32]
+    L.sr_sharded_destroy.argtypes = [vp]
+    L.sr_sharded_destroy.restype = None
+    L.sr_sharded_last_error.argtypes = [vp]
+    L.sr_sharded_last_error.restype = C.c_char_p
+    L.sr_sharded_load_features.argtypes = [vp, vp, i64, i32]
+    L.sr_sharded_song_count.argtypes = [vp]
+    L.sr_sharded_song_count.restype = i64
+    L.sr_sharded_shard_count.argtypes = [vp]
+    L.sr_sharded_engine.argtypes = [vp, i32]
+    L.sr_sharded_engine.restype = vp
+    L.sr_sharded_query_by_index.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.sr_sharded_all_pairs_topk.argtypes = [vp, i32, vp, vp]
     _lib = L
     return L
 
@@ -122,8 +140,12 @@ def _stream(stream) -> C.c_void_p:
 class Engine:
     """One scoring engine = one CUDA device (one process per GPU in multi-GPU runs)."""
 
-    def __init__(self, device: int = -1):
+    def __init__(self, device: int = -1, _borrowed=None):
         self.L = load_library()
+        self._owned = _borrowed is None
+        if _borrowed is not None:  # a shard of a ShardedEngine: options / stats only
+            self.h = C.c_void_p(_borrowed)
+            return
         h = C.c_void_p()
         rc = self.L.sr_engine_create(C.byref(h), device)
         if rc != SR_OK:
@@ -133,7 +155,8 @@ class Engine:
     # -- lifecycle -----------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "h", None):
-            self.L.sr_engine_destroy(self.h)
+            if self._owned:
+                self.L.sr_engine_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -226,6 +249,17 @@ class Engine:
         self._check(self.L.sr_engine_merge_topk_dev(self.h, _ptr(d_idx), _ptr(d_score), parts, nq, k,
                                                     _ptr(d_out_idx), _ptr(d_out_score), _stream(stream)))
 
+    def query_keys_by_vector_dev(self, d_qrows, d_exclude, nq: int, k: int, d_out_keys, d_ceil=None,
+                                 stream: int | None = None) -> None:
+        """Local top-k in the exchange format of the row-sharded path: nq x k packed 64-bit keys (0 = none)."""
+        self._check(self.L.sr_engine_query_keys_by_vector_dev(self.h, _ptr(d_qrows), _ptr(d_exclude), nq, k, _ptr(d_ceil),
+                                                              _ptr(d_out_keys), _stream(stream)))
+
+    def merge_keys_dev(self, d_keys, parts: int, nq: int, k: int, d_out_idx, d_out_score=None, stride: int = 0, col: int = 0,
+                       d_ceil_out=None, stream: int | None = None) -> None:
+        self._check(self.L.sr_engine_merge_keys_dev(self.h, _ptr(d_keys), parts, nq, k, _ptr(d_out_idx), _ptr(d_out_score),
+                                                    stride, col, _ptr(d_ceil_out), _stream(stream)))
+
     def gather_rows_dev(self, d_ids, count: int, d_out, stream: int | None = None) -> None:
         self._check(self.L.sr_engine_gather_rows_dev(self.h, _ptr(d_ids), count, _ptr(d_out), _stream(stream)))
 
@@ -257,3 +291,78 @@ class Engine:
 
     def synchronize(self) -> None:
         self._check(self.L.sr_engine_synchronize(self.h))
+
+
+class ShardedEngine:
+    """Several GPUs behind one handle in ONE process (sr_sharded_* of include/sr_engine.h): a row-sharded store
+    whose shards' top-k lists are merged over NVLink peer access, or a replicated store with sharded queries
+    (all-pairs).  `devices` lists CUDA ordinals, one shard each; an ordinal may repeat (several shards on one
+    GPU -- how the path is tested on a single-GPU box); None = every visible device."""
+
+    def __init__(self, devices=None):
+        self.L = load_library()
+        h = C.c_void_p()
+        if devices is None:
+            rc = self.L.sr_sharded_create(C.byref(h), None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.L.sr_sharded_create(C.byref(h), arr, len(devices))
+        if rc != SR_OK:
+            raise EngineError(rc, self.L.sr_sharded_last_error(None).decode())
+        self.h = h
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.L.sr_sharded_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != SR_OK:
+            raise EngineError(rc, self.L.sr_sharded_last_error(self.h).decode())
+
+    @property
+    def shard_count(self) -> int:
+        return int(self.L.sr_sharded_shard_count(self.h))
+
+    @property
+    def song_count(self) -> int:
+        return int(self.L.sr_sharded_song_count(self.h))
+
+    def shard(self, i: int) -> Engine:
+        """Shard i's engine, for set_option / stat (owned by this object)."""
+        p = self.L.sr_sharded_engine(self.h, i)
+        if not p:
+            raise IndexError(i)
+        return Engine(_borrowed=p)
+
+    def load_features(self, rows: np.ndarray, replicate: bool = False) -> None:
+        rows = np.ascontiguousarray(rows, np.float32)
+        if rows.ndim != 2 or rows.shape[1] != FEATURE_COUNT:
+            raise ValueError("rows must be (n, 12) float32")
+        self._check(self.L.sr_sharded_load_features(self.h, _ptr(rows), rows.shape[0], 1 if replicate else 0))
+
+    def query_by_index(self, qidx, k: int, scores: bool = True):
+        qidx = np.ascontiguousarray(qidx, np.int32).ravel()
+        out_i = np.empty((qidx.size, max(k, 0)), np.int32)
+        out_s = np.empty((qidx.size, max(k, 0)), np.float32) if scores else None
+        self._check(self.L.sr_sharded_query_by_index(self.h, _ptr(qidx), qidx.size, k, _ptr(out_i), _ptr(out_s)))
+        return out_i, out_s
+
+    def all_pairs_topk(self, k: int, scores: bool = True):
+        n = self.song_count
+        out_i = np.empty((n, k), np.int32)
+        out_s = np.empty((n, k), np.float32) if scores else None
+        self._check(self.L.sr_sharded_all_pairs_topk(self.h, k, _ptr(out_i), _ptr(out_s)))
+        return out_i, out_s

@@ -1,7 +1,7 @@
 """Row-sharded multi-GPU scoring (north_star (4)): one process per GPU, the
 songs split into contiguous row shards, every rank answers the whole query batch over
-its shard with GLOBAL song ids, one all-gather moves the K candidates per query, and a
-merge kernel produces the final (score desc, id asc) lists -- bit-identical to a single
+its shard with GLOBAL song ids, ONE all-gather of packed 64-bit keys moves the K candidates
+per query, and a merge kernel produces the final (score desc, id asc) lists -- bit-identical to a single
 store holding all rows, because scores do not depend on the sharding and the order is total.
 
 torch / torch.distributed are plumbing here (device buffers, the NCCL collectives over
@@ -21,8 +21,8 @@ def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
 
 
 class ShardedRecommender:
-    """`engine` needs load_features / gather_rows_dev / query_by_vector_dev /
-    merge_topk_dev (spotify_recommender_b200.engine.Engine).  `group` is a
+    """`engine` needs load_features / gather_rows_dev / query_by_vector_dev / query_keys_by_vector_dev /
+    merge_keys_dev (spotify_recommender_b200.engine.Engine).  `group` is a
     torch.distributed process group (NCCL on GPUs; the gloo tests drive the same
     host logic on CPU tensors with a checker-backed engine)."""
 
@@ -57,7 +57,7 @@ class ShardedRecommender:
     def query_by_index_dev(self, d_qidx: torch.Tensor, k: int):
         """d_qidx: int32 tensor of GLOBAL song ids, identical on every rank.  Returns
         (idx[nq,k] int32, score[nq,k] f32) device tensors, identical on every rank.
-        Stream-ordered on the current torch stream; not synchronised."""
+        Stream-ordered on the current torch stream; not synchronised.  1 <= k <= 1024."""
         nq = int(d_qidx.numel())
         st = self._stream()
         qrows = self._scratch("qrows", (nq, 12), torch.float32)
@@ -65,27 +65,30 @@ class ShardedRecommender:
         self.engine.gather_rows_dev(d_qidx, nq, qrows, st)
         if self.world > 1:
             dist.all_reduce(qrows, op=dist.ReduceOp.SUM, group=self.group)
-        # 2. local exact top-K over this shard, global ids, self excluded by global id
-        loc_i = self._scratch("loc_i", (nq, k), torch.int32)
-        loc_s = self._scratch("loc_s", (nq, k), torch.float32)
-        self.engine.query_by_vector_dev(qrows, d_qidx, nq, k, loc_i, loc_s, st)
         if self.world == 1:
+            loc_i = self._scratch("loc_i", (nq, k), torch.int32)
+            loc_s = self._scratch("loc_s", (nq, k), torch.float32)
+            self.engine.query_by_vector_dev(qrows, d_qidx, nq, k, loc_i, loc_s, st)
             return loc_i, loc_s
-        # 3. the one exchange step: K candidates per query from every shard
-        all_i = self._scratch("all_i", (self.world, nq, k), torch.int32)
-        all_s = self._scratch("all_s", (self.world, nq, k), torch.float32)
-        dist.all_gather_into_tensor(all_i.view(self.world * nq, k), loc_i, group=self.group)
-        dist.all_gather_into_tensor(all_s.view(self.world * nq, k), loc_s, group=self.group)
+        # 2. local exact top-K over this shard as packed 64-bit keys (orderable score << 32 | ~global id),
+        #    self excluded by global id
+        keys = self._scratch("keys", (nq, k), torch.int64)
+        self.engine.query_keys_by_vector_dev(qrows, d_qidx, nq, k, keys, None, st)
+        # 3. the ONE exchange step: K keys per query from every shard
+        all_keys = self._scratch("all_keys", (self.world, nq, k), torch.int64)
+        dist.all_gather_into_tensor(all_keys.view(self.world * nq, k), keys, group=self.group)
         # 4. merge (every rank ends up with the final lists)
         out_i = self._scratch("out_i", (nq, k), torch.int32)
         out_s = self._scratch("out_s", (nq, k), torch.float32)
-        self.engine.merge_topk_dev(all_i, all_s, self.world, nq, k, out_i, out_s, st)
+        self.engine.merge_keys_dev(all_keys, self.world, nq, k, out_i, out_s, 0, 0, None, st)
         return out_i, out_s
 
     def query_by_index(self, qidx, k: int):
         """Host in, host out (the end-to-end path): pinned staging, H2D of the ids,
         the device path above, D2H of the merged lists."""
         qidx = np.ascontiguousarray(qidx, np.int32).ravel()
+        if qidx.size and (qidx.min() < 0 or qidx.max() >= self.n_total):
+            raise ValueError(f"query ids must be in [0, {self.n_total})")
         nq = qidx.size
         pin = self._buf.get("pin_q")
         if pin is None or pin.numel() != nq:
@@ -106,3 +109,49 @@ class ShardedRecommender:
         if self.device.type == "cuda":
             torch.cuda.current_stream().synchronize()
         return h_i.numpy().copy(), h_s.numpy().copy()
+
+
+class QueryShardedAllPairs:
+    """BASELINE config 5 on several GPUs (SURVEY 8e "All-pairs"): the store is REPLICATED (48 B/song: 48 MB at
+    1 M songs), rank r computes the neighbour lists of the query songs [r * ceil(N/G), ...) with the same
+    kernels and no exchange at all; one all-gather at the very end assembles the N x K table on every rank."""
+
+    def __init__(self, engine, group=None, device=None):
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.n = 0
+
+    def load_replicated(self, rows) -> None:
+        """rows: ALL rows, the same on every rank."""
+        self.engine.load_features(rows, id_base=0)
+        self.n = int(rows.shape[0])
+
+    def local_range(self) -> tuple[int, int]:
+        return shard_bounds(self.n, self.world, self.rank)
+
+    def local_topk(self, k: int):
+        """This rank's slice of the table (host arrays); empty slices give (0, k) arrays."""
+        lo, hi = self.local_range()
+        if hi <= lo:
+            return np.empty((0, k), np.int32), np.empty((0, k), np.float32)
+        return self.engine.all_pairs_topk(lo, hi, k)
+
+    def all_pairs_topk(self, k: int):
+        """(idx[N,k] int32, score[N,k] f32) host arrays, identical on every rank."""
+        li, ls = self.local_topk(k)
+        if self.world == 1:
+            return li, ls
+        per = -(-self.n // self.world)
+        pad_i = torch.full((per, k), -1, dtype=torch.int32)
+        pad_s = torch.zeros((per, k), dtype=torch.float32)
+        pad_i[:li.shape[0]] = torch.from_numpy(li)
+        pad_s[:ls.shape[0]] = torch.from_numpy(ls)
+        d_i, d_s = pad_i.to(self.device), pad_s.to(self.device)
+        all_i = torch.empty((self.world * per, k), dtype=torch.int32, device=self.device)
+        all_s = torch.empty((self.world * per, k), dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(all_i, d_i, group=self.group)
+        dist.all_gather_into_tensor(all_s, d_s, group=self.group)
+        return all_i[:self.n].cpu().numpy(), all_s[:self.n].cpu().numpy()

@@ -30,9 +30,10 @@ def test_class_mirrors_reference_api(oracle, names):
     rec = HostRecommender(f, ids=ids, names=names)
     assert rec.gpu_enabled()
     # by index: canonical order == oracle
-    for q, k in ((0, 10), (17, 1), (2999, 100), (5, 4000)):
-        want, _ = oracle.query_index(f, [q], min(k, 1024))
+    for q, k in ((0, 10), (17, 1), (2999, 100), (5, 1500), (5, 4000)):  # topN > N - 1 yields N - 1 results (Recommender.cu:300-315)
+        want, _ = oracle.query_index(f, [q], k)
         got = rec.by_index(q, k)
+        assert got.size == min(k, 2999)
         assert np.array_equal(got, want[0][want[0] >= 0])
     # error behaviour (reference Recommender.cu:276-284, :358-361, :367-370): empty result
     assert rec.by_index(-1, 5).size == 0 and rec.by_index(3000, 5).size == 0 and rec.by_index(3, 0).size == 0

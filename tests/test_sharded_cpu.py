@@ -45,6 +45,41 @@ class CheckerEngine:
         d_out_idx.copy_(torch.from_numpy(mi))
         d_out_score.copy_(torch.from_numpy(ms))
 
+    # the exchange format of the row-sharded path: orderable(score + 0.0) << 32 | (0xFFFFFFFF - id), 0 = none
+    def query_keys_by_vector_dev(self, d_qrows, d_excl, nq, k, d_out_keys, d_ceil=None, stream=0):
+        ex = d_excl.numpy().astype(np.int64) - self.base
+        ex[(ex < 0) | (ex >= self.rows.shape[0])] = -1
+        oi, os_ = self.o.query_rows(self.rows, d_qrows.numpy(), ex, k, id_base=self.base)
+        d_out_keys.copy_(torch.from_numpy(pack_keys(oi, os_)))
+
+    def merge_keys_dev(self, d_keys, parts, nq, k, d_out_idx, d_out_score=None, stride=0, col=0, d_ceil_out=None, stream=0):
+        idx, score = unpack_keys(d_keys.numpy().reshape(parts, nq, k))
+        mi, ms = self.o.merge_parts(idx, score)
+        d_out_idx.copy_(torch.from_numpy(mi))
+        d_out_score.copy_(torch.from_numpy(ms))
+
+    def all_pairs_topk(self, lo, hi, k, scores=True):
+        return self.o.query_index(self.rows, np.arange(lo, hi, dtype=np.int32), k)
+
+
+def pack_keys(idx, score):
+    u = (score + np.float32(0.0)).view(np.uint32).astype(np.uint64)
+    o = np.where(u & 0x80000000, ~u & 0xFFFFFFFF, u | 0x80000000).astype(np.uint64)
+    key = (o << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - idx.astype(np.int64).astype(np.uint64) & np.uint64(0xFFFFFFFF))
+    key[idx < 0] = 0
+    return key.view(np.int64)
+
+
+def unpack_keys(key):
+    key = np.ascontiguousarray(key).view(np.uint64)
+    o = (key >> np.uint64(32)).astype(np.uint32)
+    u = np.where(o & 0x80000000, o ^ 0x80000000, ~o).astype(np.uint32)
+    idx = (np.uint64(0xFFFFFFFF) - (key & np.uint64(0xFFFFFFFF))).astype(np.int64).astype(np.int32)
+    score = u.view(np.float32).copy()
+    idx[key == 0] = -1
+    score[key == 0] = 0.0
+    return idx, score
+
 
 def _worker(rank, world, port, n, k, out_dir):
     sys.path.insert(0, HERE)
