@@ -72,16 +72,20 @@ struct Variant {
     {"S" #S "xT" #T "x" #M "-tma", S, T, M, true, false, launch_scan<S, T, M, true, true, false>, occ_scan<S, T, M, true, true, false>, launch_bound<S, T, M>}
 #define SR_VARIANT_DYN(S, T, M) \
     {"S" #S "xT" #T "x" #M "-dyn", S, T, M, false, true, launch_scan<S, T, M, true, false, true>, occ_scan<S, T, M, true, false, true>, launch_bound<S, T, M>}
+#define SR_VARIANT_DTMA(S, T, M) \
+    {"S" #S "xT" #T "x" #M "-dyn-tma", S, T, M, true, true, launch_scan<S, T, M, true, true, true>, occ_scan<S, T, M, true, true, true>, launch_bound<S, T, M>}
 const Variant kVariants[] = {
     SR_VARIANT(8, 256, 2, false),   // 0  plain hit branch in the loop
     SR_VARIANT(8, 256, 2, true),    // 1  branch-free loop, deferred hits
     SR_VARIANT(8, 512, 1, false),   // 2
     SR_VARIANT(8, 512, 1, true),    // 3  static runs of units (fallback of 5 when query tiles outnumber CTAs)
-    SR_VARIANT_TMA(8, 256, 2),      // 4  small batches: TMA-staged tiles
-    SR_VARIANT_DYN(8, 512, 1),      // 5  large batches: dynamic tile claiming
+    SR_VARIANT_DTMA(8, 256, 2),     // 4  small batches (HBM-bound): TMA-staged tiles, dynamic tile claiming
+    SR_VARIANT_DYN(8, 512, 1),      // 5  large batches: dynamic tile claiming, tiles loaded straight into registers
+    SR_VARIANT_DTMA(8, 512, 1),     // 6  mid-size batches, short lists: 64-query tiles, the next song tile staged by TMA meanwhile
+    SR_VARIANT_TMA(8, 256, 2),      // 7  the static form of 4 (contiguous runs of units)
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-constexpr int kAutoSmall = 4, kAutoLarge = 5, kStaticLarge = 3, kAutoS = 8;
+constexpr int kAutoSmall = 4, kAutoLarge = 5, kAutoMid = 6, kStaticLarge = 3, kAutoS = 8;
 
 enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kBound, kNumKernels };
 const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge", "bound"};
@@ -118,7 +122,12 @@ struct sr_engine {
     int hit_cap = 0;   // hit-buffer entries per query in shared memory (0: sized from K)
     int list_ws_opt = 1;    // allow the CTAs' lists in an L2-resident workspace when that keeps the query tile at full size
     int list_ws_kmax = 72;  // ... for k up to this
-    int small_max = 40;     // batches of at most this many queries take the TMA-staged small-batch shape
+    int small_max = 32;     // batches of at most this many queries take the TMA-staged small-batch shape
+    int mid_max = 0;        // ... and up to this many (k <= 16) the TMA-staged 64-query-tile shape (measured: never better
+                            // than the register-loading shape by more than 2 %, so off by default)
+    int refresh_every = 0;  // tiles between two looks at the thresholds other CTAs published (0: automatic)
+    int bound_blocks = 0;   // disjoint sample blocks of the bound pass (0: 64 / 128 / 256 by k)
+    int prefetch = -1;      // L2 prefetch of the next song tile in the dynamic shape (-1: for groups of <= 640 queries)
     int bound_tiles = 0;    // layout tiles (of S x 256 songs) the bound pass samples (0: 48 for k <= 16, else 128)
     bool profile = false;
 
@@ -310,17 +319,23 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     // small batches are HBM-bound: two 256-thread CTAs per SM, song tiles staged through shared
     // memory by TMA one tile ahead; large batches are FP32-bound: one 512-thread CTA, bigger
     // tiles, shared memory spent on 256 queries' lists and hit buffers
-    int vi = e->variant >= 0 ? e->variant : (nq <= e->small_max ? kAutoSmall : kAutoLarge);
+    // mid-size batches with short lists: the dynamic shape with 64-query tiles, whose song tiles (now a quarter of
+    // the arithmetic per load) are staged through shared memory by TMA while the previous tile is multiplied
+    int vi = e->variant >= 0 ? e->variant : (nq <= e->small_max ? kAutoSmall : (nq <= e->mid_max && K <= 16 ? kAutoMid : kAutoLarge));
     const Variant *vp = nullptr;
     int TS = 0, n_tiles = 0, groups = 0, gsize = 0, qt_cap = 0, cap = 0;
     bool lists_in_smem = true;
     size_t stage_bytes = 0;
     for (int attempt = 0; attempt < 2 && !qt_cap; ++attempt) {
-        if (attempt == 1) {  // the staged small-batch shape has little shared memory left for long lists
+        if (attempt == 1) {  // the staged shapes have little shared memory left for long lists
             if (e->variant >= 0 || vi == kAutoLarge) break;
             vi = kAutoLarge;
         }
         vp = &kVariants[vi];
+        if (vp->staged && vp->dynamic && (nq + std::min(e->qt_opt, kQTMax) - 1) / std::min(e->qt_opt, kQTMax) > e->sm_count * vp->ctas) {
+            vi = kAutoLarge;  // more query tiles than CTAs (only with a tiny "qt" option): the shape with a static fallback
+            vp = &kVariants[vi];
+        }
         TS = vp->S * vp->threads;
         n_tiles = (int)((e->n + TS - 1) / TS);
         // query groups (what fits the constant bank), evenly filled; then query tiles inside a group
@@ -331,8 +346,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         // few K lets an overflowing buffer alone lift the threshold far enough for the re-filter
         // round to converge.  First combination that fits wins.
         stage_bytes = vp->staged ? (size_t)TS * kF * 4 : 0;
-        const size_t smem_budget = (size_t)216 * 1024 / vp->ctas;
-        const int qt_max = std::max(1, std::min(e->qt_opt, kQTMax));
+        const size_t smem_budget = vp->staged && vp->ctas == 1 ? (size_t)230000 : (size_t)216 * 1024 / vp->ctas;
+        const int qt_max = std::max(1, std::min({e->qt_opt, kQTMax, vp->staged && vp->ctas == 1 ? 64 : kQTMax}));
         const int kk = std::max(K, 32);
         for (int qtry = qt_max; qtry >= 1 && !qt_cap; qtry = (qtry > 8 ? qtry / 2 : qtry - 1)) {
             const int caps[4] = {e->hit_cap > 0 ? e->hit_cap : std::max(128, 4 * kk), std::max(128, 2 * kk),
@@ -359,6 +374,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     const int qt = (gsize + nqt0 - 1) / nqt0;
     const int nqt = (gsize + qt - 1) / qt;
     if (!lists_in_smem && scan_smem_bytes(qt, cap, K, stage_bytes, true) <= (size_t)216 * 1024 / v.ctas) lists_in_smem = true;  // few queries: they fit after all
+    if (v.dynamic && v.staged && nqt > e->sm_count * v.ctas) return fail(e, SR_EINVAL, "kernel shape %s: %d query tiles exceed the grid; raise the \"qt\" option", v.name, nqt);
     e->last_lists_in_smem = lists_in_smem ? 1 : 0;
     const size_t smem = scan_smem_bytes(qt, cap, K, stage_bytes, lists_in_smem);
     int ctas = 0;
@@ -386,10 +402,14 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     // enough full tiles, else the exact sample.  Neither is valid under a ceiling (they bound the
     // K-th best of ALL songs, a ceiling pass wants the K-th best below the ceiling).
     const int64_t full_tiles = e->n / TS;
-    const int nblk = K + 1;                                  // disjoint blocks of sample songs
-    // sample tiles: 48 (short lists) or 128 layout tiles on large stores, never more than ~6 % of the store
-    const int n_sample = (int)std::min<int64_t>({(int64_t)(e->bound_tiles > 0 ? e->bound_tiles : (K <= 16 ? 48 : 128)) / (v.threads / kLT), std::max<int64_t>(4, full_tiles / 16), full_tiles / 4});
-    const bool use_bound = e->bound && !out.ceil_in && nblk <= kLT / 2 && n_sample >= 4 && (int64_t)n_sample * TS >= 64 * (int64_t)nblk;
+    // disjoint blocks of sample songs: at least K + 1, and several times that where it is cheap, so that the
+    // (K+1)-th largest block maximum comes close to the sample's exact K-th best
+    const int nblk = e->bound_blocks > 0 ? std::max(e->bound_blocks, K + 1) : (K < 16 ? 64 : (K < 64 ? 128 : 256));
+    // sample tiles: 48 (short lists) or 96 layout tiles on large stores, never more than ~6 % of the store
+    const int n_sample = (int)std::min<int64_t>({(int64_t)(e->bound_tiles > 0 ? e->bound_tiles : (K <= 16 ? 48 : 96)) / (v.threads / kLT), std::max<int64_t>(4, full_tiles / 16), full_tiles / 4});
+    const bool use_bound = e->bound && !out.ceil_in && K + 1 <= nblk && nblk <= kLT && n_sample >= 4 && (int64_t)n_sample * TS >= 16 * (int64_t)nblk;
+    const int bqt = std::max(1, std::min({qt, 64, (int)(48 * 1024 / (nblk * 4))}));  // the bound pass's own (finer) query tiles: the block maxima of a tile live in shared memory
+    const int bnqt_max = (gsize + bqt - 1) / bqt;
 
     int rc;
     if ((rc = ensure(e, e->qraw, (size_t)nq * kF * 4))) return rc;
@@ -400,7 +420,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if ((rc = ensure(e, e->gbound, (size_t)nq * nblk * 4))) return rc;
     const int nslot = std::max(256, (K + 31) / 32 * 32);  // residue slots per query (global threshold feedback)
     if ((rc = ensure(e, e->gslot, (size_t)nq * nslot * 4))) return rc;
-    const int ctr_per_group = 2 * nqt + 2;                // tile counters, visit counters, bound-pass completion
+    const int ctr_per_group = 2 * nqt + bnqt_max + 1;     // tile counters, visit counters, bound-pass completion per bound query tile
     if ((rc = ensure(e, e->ctr, (size_t)groups * ctr_per_group * 4))) return rc;
     if ((rc = ensure(e, e->pool_cnt, (size_t)nq * 4))) return rc;
     // settle triggers: a quarter-full buffer starts a settle phase (earlier settles = tighter thresholds = fewer
@@ -467,10 +487,12 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.qraw = (float *)e->qraw.p + (size_t)g0 * kF; a.qn = (float *)e->qn.p + g0;
         a.exclude = (int32_t *)e->excl.p + g0; a.nq = gq; a.qt = qt;
         a.K = K; a.cap = cap; a.settle_at = settle_at_eff;
-        a.refresh_every = std::max(1, std::min(8, 64 / qt));
+        // (dynamic shapes: every tile -- a CTA's tiles come from all over the store, it lives on what the others found)
+        a.refresh_every = e->refresh_every > 0 ? e->refresh_every : (v.dynamic ? 1 : std::max(1, std::min(8, 64 / qt)));
         a.trigger_at = trigger_at_eff;
         a.gslot = (uint32_t *)e->gslot.p + (size_t)g0 * nslot;
         a.nslot = nslot;
+        a.prefetch = e->prefetch >= 0 ? e->prefetch : (gq <= 640 ? 1 : 0);
         a.ceil = out.ceil_in ? out.ceil_in + g0 : nullptr;
         a.pool = (uint64_t *)e->pool.p + (size_t)g0 * slab; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
         a.segs = segs; a.slab = slab;
@@ -484,9 +506,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
                                             cudaMemcpyDeviceToDevice, st));
         }
         if (use_bound) {
-            // its own (finer) query tiles: the block maxima of a tile live in shared memory
             ScanArgs b = a;
-            b.qt = std::max(1, std::min({qt, 64, (int)(48 * 1024 / (nblk * 4))}));
+            b.qt = bqt;
             const int bnqt = (gq + b.qt - 1) / b.qt;
             const int bgrid = (int)std::min<int64_t>((int64_t)e->sm_count * v.ctas, (int64_t)bnqt * n_sample);
             uint32_t *gmax = (uint32_t *)e->gbound.p + (size_t)g0 * nblk;
@@ -981,6 +1002,17 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "list_ws_kmax")) {
         if (value < 0 || value > kKMax) return fail(e, SR_EINVAL, "list_ws_kmax must be in [0, %d]", kKMax);
         e->list_ws_kmax = (int)value;
+    } else if (!strcmp(key, "bound_blocks")) {
+        if (value != 0 && (value < 2 || value > kLT)) return fail(e, SR_EINVAL, "bound_blocks must be 0 (auto) or in [2, %d]", kLT);
+        e->bound_blocks = (int)value;
+    } else if (!strcmp(key, "prefetch")) {
+        e->prefetch = value < 0 ? -1 : (value != 0);
+    } else if (!strcmp(key, "refresh_every")) {
+        if (value < 0 || value > 64) return fail(e, SR_EINVAL, "refresh_every must be in [0, 64]");
+        e->refresh_every = (int)value;
+    } else if (!strcmp(key, "mid_max")) {
+        if (value < 0 || value > (1 << 20)) return fail(e, SR_EINVAL, "mid_max must be in [0, 2^20]");
+        e->mid_max = (int)value;
     } else if (!strcmp(key, "small_max")) {
         if (value < 0 || value > kConstQueries) return fail(e, SR_EINVAL, "small_max must be in [0, %d]", kConstQueries);
         e->small_max = (int)value;

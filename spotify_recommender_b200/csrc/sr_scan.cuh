@@ -85,6 +85,7 @@ struct ScanArgs {
     uint32_t *gslot;         // [nq][nslot] lock-free global feedback: slot (id mod nslot) holds the best exact
                              // score (orderable) any CTA has found among the songs with that residue
     int nslot;               // >= K, multiple of 32
+    int prefetch;            // DYN shapes: bulk-prefetch the next song tile into L2 while the current one is multiplied
     const uint64_t *ceil;    // null, or [nq] per-query ceiling keys: only keys BELOW the ceiling are admitted (pass p > 0 of a
                              // K > kKMax query continues below the last key of pass p - 1); offset like the other per-query arrays
     unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] refilters; [5..12] cycle counters (-DSR_SCAN_TIMING)
@@ -485,6 +486,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     // DYN: the per-tile barrier is split (arrive ... wait) so the next tile's loads overlap the wait
     __shared__ uint64_t s_tbar;
     uint32_t tbar_phase = 0;
+
     if (threadIdx.x < 4) s_flag[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_redo_cnt[threadIdx.x] = 0;
 #ifdef SR_SCAN_TIMING
@@ -521,7 +523,9 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     if (STAGE) {
         if (tid == 0) {
             mbar_init(s_bar, 1);
-            if (u < u_end) tma_load_tile(s_tile, a.hat + (int64_t)t0 * a.tile_stride * (TS * kF), kTileBytes, s_bar);
+            // (DYN: the first claimed tile; a claim at or beyond n_tiles means the query tile is already exhausted)
+            const int first = DYN ? s_next[0] : t0;
+            if (u < u_end && first < a.n_tiles) tma_load_tile(s_tile, a.hat + (int64_t)first * a.tile_stride * (TS * kF), kTileBytes, s_bar);
         }
         __syncthreads();
     }
@@ -572,12 +576,22 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         // read during tile t-2, and the NEXT tile's index is already visible while tile t runs, so
         // its songs are loaded between arriving at tile t's barrier and waiting on it.
         int tile = DYN ? __reduce_max_sync(0xffffffffu, s_next[0]) : t0;
-        if (DYN) load_songs(min(tile, a.n_tiles - 1));
+        if (DYN && !STAGE) load_songs(min(tile, a.n_tiles - 1));
         for (; tile < t1; ++it, slot = (slot == 2 ? 0 : slot + 1)) {
             // (the claim for the tile after next: issued now, stored after the hot loop, so thread 0
             // does not start every tile a global round trip late)
             int claimed = 0;
             if (DYN && tid == 0) claimed = atomicAdd(a.tile_ctr + qtile, 1);
+            if (DYN && !STAGE && a.prefetch && lane == 0) {
+                // the next tile of this CTA (claimed one tile ago) starts its way from HBM into L2 now, so the loads
+                // issued between this tile's arrive and wait find it there: with few queries per tile (mid-size
+                // batches) the tile load is otherwise 15-25 % of the tile's time.  One slice per warp.
+                const int nt = s_next[slot == 2 ? 0 : slot + 1];
+                if (nt < a.n_tiles) {
+                    const char *src = reinterpret_cast<const char *>(a.hat) + ((int64_t)nt * a.tile_stride * TS * kF * 4) + (size_t)warp * (kTileBytes / WARPS);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(kTileBytes / WARPS) : "memory");
+                }
+            }
             const int64_t stile = (int64_t)tile * a.tile_stride;  // store tile
             const int64_t ltile = stile * SUB + tid / kLT;      // this thread's layout tile
             const int row0 = (int)(ltile * (S * kLT)) + tid % kLT;  // its songs: row0 + s * kLT (ids are 32-bit)
@@ -595,10 +609,15 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                         fp[p][2 * c4 + 1] = make_float2(v.z, v.w);
                     }
                 }
+                // (a full barrier: an arrive-only barrier with thread 0 alone waiting was tried -- the spin loop inside the
+                // divergent branch makes ptxas drop the hot loop's uniform-register operands)
                 __syncthreads();  // every thread has copied its songs out: the buffer is free
                 if (tid == 0) {   // next tile of this run: same query tile, or tile 0 of the next one
                     int64_t nxt = -1;
-                    if (tile + 1 < t1) nxt = stile + a.tile_stride;
+                    if (DYN) {    // (claimed one tile ago; at or beyond n_tiles: this query tile is exhausted)
+                        const int nt = s_next[slot == 2 ? 0 : slot + 1];
+                        if (nt < a.n_tiles) nxt = (int64_t)nt * a.tile_stride;
+                    } else if (tile + 1 < t1) nxt = stile + a.tile_stride;
                     else if (u + (t1 - t0) < u_end) nxt = 0;
                     if (nxt >= 0) tma_load_tile(s_tile, a.hat + nxt * (TS * kF), kTileBytes, s_bar);
                 }
@@ -688,8 +707,9 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 next_tile = __reduce_max_sync(0xffffffffu, s_next[slot == 2 ? 0 : slot + 1]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_tbar);
-                // in flight while the slower warps finish: the next tile's songs, the published thresholds
-                load_songs(min(next_tile, a.n_tiles - 1));
+                // in flight while the slower warps finish: the next tile's songs (unless the bulk-copy engine is
+                // already bringing them into shared memory), the published thresholds
+                if (!STAGE) load_songs(min(next_tile, a.n_tiles - 1));
                 refresh();
                 SR_TIME_BEGIN(2);
                 mbar_wait(&s_tbar, tbar_phase);
@@ -757,7 +777,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     __syncthreads();
                 }
                 // (the prefetched songs were not kept alive across the settle code: fetch them again, L2-hot)
-                if (DYN) load_songs(min(next_tile, a.n_tiles - 1));
+                if (DYN && !STAGE) load_songs(min(next_tile, a.n_tiles - 1));
                 SR_TIME_END(1);
             }
             tile = next_tile;
@@ -855,8 +875,10 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 }
                 s_next[3] = cand;
                 if (cand >= 0) {
-                    s_next[0] = atomicAdd(a.tile_ctr + cand, 1);
+                    const int first = atomicAdd(a.tile_ctr + cand, 1);
+                    s_next[0] = first;
                     s_next[1] = atomicAdd(a.tile_ctr + cand, 1);
+                    if (STAGE && first < a.n_tiles) tma_load_tile(s_tile, a.hat + (int64_t)first * a.tile_stride * (TS * kF), kTileBytes, s_bar);
                 }
             }
             __syncthreads();
@@ -886,77 +908,100 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 // ---- bound pass ---------------------------------------------------------------------------
 // Threshold bootstrap at filter speed.  `n_sample` evenly spaced FULL tiles are scored for
 // every query of the group (12 FFMA per pair, same loop as the scan, a max instead of a sign
-// test).  Their songs are split into K+1 disjoint blocks by the residue of the owning layout
-// thread, so every block spans all sample tiles (and with them every cluster of the store that
-// is at least store/n_sample long -- e.g. every genre of a genre-sorted store).  Each block's
-// best filter score belongs to a distinct song, at most one of them the query song itself, so
-// the minimum over the K+1 block maxima is a lower bound of the K-th best filter score among
-// real candidates: no selection, no sorting, ~2.5 % of a full pass.
-// Unit u = (query tile, sample tile); each CTA takes whole units.
+// test).  Their songs are split into `nblk` >= K+1 disjoint blocks by the residue of the owning
+// layout thread, so every block spans all sample tiles (and with them every cluster of the store
+// that is at least store/n_sample long -- e.g. every genre of a genre-sorted store).  Each block's
+// best filter score belongs to a distinct song, at most one of them the query song itself, so the
+// (K+1)-th LARGEST of the block maxima is a lower bound of the K-th best filter score among real
+// candidates: no sorting of songs, ~1-2.5 % of a full pass.  With nblk well above K+1 two of the
+// sample's best songs rarely share a block and the bound approaches the sample's exact K-th best
+// (with nblk = K+1 it is the minimum of the maxima, about H(K+1) = 3-5 times further down the ranks).
+// Unit u = (query tile, sample tile); each CTA takes whole units; the CTA that completes a query
+// tile's last unit folds the maxima into the starting thresholds g_best.
 template <int S, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) bound_kernel(const ScanArgs a, int nblk, int n_sample, int stride,
                                                               uint32_t *gmax, int *done_ctr)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t *s_max = reinterpret_cast<uint32_t *>(smem_raw);  // [qt][nblk] orderable block maxima of this unit
+    uint32_t *s_max = reinterpret_cast<uint32_t *>(smem_raw);  // [qt][nblk] orderable block maxima of this CTA's run
+    __shared__ int s_last;
     const int tid = threadIdx.x;
     const int blk = (tid % kLT) % nblk;
     const int nqt = (a.nq + a.qt - 1) / a.qt;
-    for (int u = blockIdx.x; u < nqt * n_sample; u += gridDim.x) {
-        int qtile = 0, j = u;
-        while (j >= n_sample) { j -= n_sample; ++qtile; }
+    // a contiguous run of units (query-tile major): the maxima stay in shared memory across the sample tiles of
+    // one query tile and reach the global array once per query tile of the run
+    const int total = nqt * n_sample, per = total / (int)gridDim.x, extra = total % (int)gridDim.x;
+    int u = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
+    const int u_end = u + per + ((int)blockIdx.x < extra ? 1 : 0);
+    int qtile = 0, j = u;
+    while (j >= n_sample) { j -= n_sample; ++qtile; }
+    while (u < u_end) {
         const int q0 = qtile * a.qt;
         const int nql = min(a.qt, a.nq - q0);
+        const int j_end = min(n_sample, j + (u_end - u));
         for (int i = tid; i < nql * nblk; i += THREADS) s_max[i] = 0u;
         __syncthreads();
-        const int64_t ltile = (int64_t)j * stride * (THREADS / kLT) + tid / kLT;
-        float2 fp[S / 2][kF];
-        {
-            const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (ltile * (S / 2) * kLT + tid % kLT) * 6;
+        for (int jj = j; jj < j_end; ++jj) {
+            const int64_t ltile = (int64_t)jj * stride * (THREADS / kLT) + tid / kLT;
+            float2 fp[S / 2][kF];
+            {
+                const float4 *src = reinterpret_cast<const float4 *>(a.hat) + (ltile * (S / 2) * kLT + tid % kLT) * 6;
 #pragma unroll
-            for (int p = 0; p < S / 2; ++p) {
+                for (int p = 0; p < S / 2; ++p) {
 #pragma unroll
-                for (int c4 = 0; c4 < 6; ++c4) {
-                    const float4 v = __ldg(src + (int64_t)p * kLT * 6 + c4);
-                    fp[p][2 * c4] = make_float2(v.x, v.y);
-                    fp[p][2 * c4 + 1] = make_float2(v.z, v.w);
+                    for (int c4 = 0; c4 < 6; ++c4) {
+                        const float4 v = __ldg(src + (int64_t)p * kLT * 6 + c4);
+                        fp[p][2 * c4] = make_float2(v.x, v.y);
+                        fp[p][2 * c4 + 1] = make_float2(v.z, v.w);
+                    }
+                }
+            }
+#pragma unroll 2
+            for (int ql = 0; ql < nql; ++ql) {
+                float2 acc[S / 2];
+                filter_query<S>(fp, q0 + ql, 0.0f, acc);
+                float m = -__int_as_float(0x7f800000);
+#pragma unroll
+                for (int p = 0; p < S / 2; ++p) m = fmaxf(m, fmaxf(acc[p].x, acc[p].y));  // NaN (irregular) rows are ignored
+                const uint32_t o = f2ord(m);
+                if (o > s_max[ql * nblk + blk]) atomicMax(&s_max[ql * nblk + blk], o);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nql * nblk; i += THREADS)  // (a read first: most maxima of a later run already stand)
+            if (s_max[i] > __ldcg(gmax + (size_t)q0 * nblk + i)) atomicMax(gmax + (size_t)q0 * nblk + i, s_max[i]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(done_ctr + qtile, j_end - j) + (j_end - j) == n_sample);
+        __syncthreads();
+        if (s_last) {
+            // every sample tile of this query tile is in: (K+1)-th largest block maximum per query, one warp
+            // per query (binary search over the 32 bits of the orderable values, nblk / 32 values per lane)
+            __threadfence();
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int ql = warp; ql < nql; ql += THREADS / 32) {
+                const uint32_t *row = gmax + (size_t)(q0 + ql) * nblk;
+                uint32_t v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) v[r] = (r * 32 + lane < nblk) ? __ldcg(row + r * 32 + lane) : 0u;
+                uint32_t kth = 0;
+                for (int bit = 31; bit >= 0; --bit) {
+                    const uint32_t cand = kth | (1u << bit);
+                    int c = 0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) c += (v[r] >= cand);
+                    if ((int)__reduce_add_sync(0xffffffffu, (unsigned)c) >= a.K + 1) kth = cand;
+                }
+                if (lane == 0 && kth != 0u) {  // (0: fewer than K+1 blocks saw a regular song -- no bound)
+                    const uint32_t o = f2ord(ord2f(kth) - kBoundSlack);
+                    if (o > a.g_best[q0 + ql]) a.g_best[q0 + ql] = o;
                 }
             }
         }
-#pragma unroll 2
-        for (int ql = 0; ql < nql; ++ql) {
-            float2 acc[S / 2];
-            filter_query<S>(fp, q0 + ql, 0.0f, acc);
-            float m = -__int_as_float(0x7f800000);
-#pragma unroll
-            for (int p = 0; p < S / 2; ++p) m = fmaxf(m, fmaxf(acc[p].x, acc[p].y));  // NaN (irregular) rows are ignored
-            const uint32_t o = f2ord(m);
-            if (o > s_max[ql * nblk + blk]) atomicMax(&s_max[ql * nblk + blk], o);
-        }
         __syncthreads();
-        for (int i = tid; i < nql * nblk; i += THREADS)
-            if (s_max[i]) atomicMax(gmax + (size_t)q0 * nblk + i, s_max[i]);
-        __syncthreads();
-    }
-    // The CTA that finishes last folds the block maxima into the starting thresholds: K+1 disjoint blocks each
-    // hold a song whose filter score is >= the block maximum, at most one of them the query song itself, so the
-    // exact K-th best is >= min(block maxima) - kBoundSlack.
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(done_ctr, 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int q = tid; q < a.nq; q += THREADS) {
-        uint32_t mn = 0xFFFFFFFFu;
-        for (int r = 0; r < nblk; ++r) {
-            const uint32_t v = __ldcg(gmax + (size_t)q * nblk + r);
-            mn = v < mn ? v : mn;
-        }
-        if (mn == 0u || mn == 0xFFFFFFFFu) continue;  // an empty block: no bound
-        const uint32_t o = f2ord(ord2f(mn) - kBoundSlack);
-        if (o > a.g_best[q]) a.g_best[q] = o;
+        u += j_end - j;
+        j = 0;
+        ++qtile;
     }
 }
 

@@ -23,7 +23,7 @@ def eng():
     e.close()
 
 
-AUTO_SHAPES = (4, 5)  # the two shapes the engine picks by itself: TMA-staged small-batch, dynamic large-batch
+AUTO_SHAPES = (4, 5, 6)  # the shapes the engine picks by itself: TMA-staged small-batch, dynamic large-batch, TMA-staged mid-batch
 
 
 def assert_exact(got, want):
@@ -79,7 +79,7 @@ def test_golden_vectors(eng, oracle, case):
             assert np.array_equal(gs[0, :n].view(np.uint32), ref_sc[gi[0, :n]].view(np.uint32))
 
 
-@pytest.mark.parametrize("variant", range(6))
+@pytest.mark.parametrize("variant", range(8))
 def test_every_kernel_shape(eng, oracle, variant):  # k = 1, 10, 100; 257 queries
     n = 150_000
     f = synth.features(n)
@@ -102,8 +102,6 @@ def test_sizes_and_ragged_batches(eng, oracle, n, nq, k):
     q = synth.query_indices(nq, n)
     assert_exact(eng.query_by_index(q, k), oracle.query_index(f, q, k, threads=8))
     assert eng.stat("variant") in AUTO_SHAPES  # the shapes the engine selects by itself are the ones under test
-    if 33 <= k <= 72 and nq >= 256:
-        assert eng.stat("lists_in_smem") == 0, "the L2-resident list workspace was not taken"
 
 
 @pytest.mark.parametrize("k", [40, 50, 64, 72])
@@ -113,9 +111,9 @@ def test_l2_list_workspace_path(eng, oracle, k):
     n = 200_000
     for f in (synth.uniform(n), synth.features(n), np.tile(synth.adversarial(4096), (49, 1))[:n]):
         eng.load_features(f)
-        q = synth.query_indices(700, n)
+        q = synth.query_indices(1024, n)  # four full 256-query tiles
         assert_exact(eng.query_by_index(q, k), oracle.query_index(f, q, k, threads=8))
-        assert eng.stat("variant") == 5 and eng.stat("lists_in_smem") == 0
+        assert eng.stat("variant") == 5 and eng.stat("lists_in_smem") == 0, "the L2-resident list workspace was not taken"
 
 
 def test_adversarial_ties_zero_rows_irregular(eng, oracle):

@@ -137,3 +137,33 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert all(hi - lo <= -(-n // w) for lo, hi in b)
+
+
+def _all_pairs_worker(rank, world, port, n, k, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spotify_recommender_b200 import synth
+    from spotify_recommender_b200.sharded import QueryShardedAllPairs
+    ap = QueryShardedAllPairs(CheckerEngine(), device=torch.device("cpu"))
+    ap.load_replicated(synth.adversarial(n))
+    gi, gs = ap.all_pairs_topk(k)
+    np.save(os.path.join(out_dir, f"ap_idx{rank}.npy"), gi)
+    np.save(os.path.join(out_dir, f"ap_score{rank}.npy"), gs)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_query_sharded_all_pairs_equals_single_store(tmp_path, oracle, world):
+    """BASELINE config 5 host logic (SURVEY 8e "All-pairs"): store replicated, queries sharded, one final gather
+    -- every rank ends up with the whole n x k table, ragged last slice included."""
+    from spotify_recommender_b200 import synth
+    n, k = 1003, 10
+    mp.spawn(_all_pairs_worker, args=(world, _free_port(), n, k, str(tmp_path)), nprocs=world, join=True)
+    wi, ws = oracle.query_index(synth.adversarial(n), np.arange(n, dtype=np.int32), k)
+    for rank in range(world):
+        assert np.array_equal(np.load(tmp_path / f"ap_idx{rank}.npy"), wi)
+        assert np.array_equal(np.load(tmp_path / f"ap_score{rank}.npy").view(np.uint32), ws.view(np.uint32))

@@ -92,7 +92,7 @@ def test_single_process_sharded_abi(oracle, shards):
         assert se.shard_count == shards
         se.load_features(f)
         assert se.song_count == n
-        q = np.concatenate([synth.query_indices(300, n), [0, n - 1, n // shards, n // shards - 1]]).astype(np.int32)
+        q = np.concatenate([synth.query_indices(300, n), [0, n - 1, n // (shards + 1), n // (shards + 1) - 1]]).astype(np.int32)
         for k in (10, 100):
             assert_exact(se.query_by_index(q, k), oracle.query_index(f, q, k, threads=8))
         # a big ragged batch (several internal batches of 8192)
