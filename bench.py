@@ -23,6 +23,7 @@ Extra keys on the same line (DESIGN.md "measurement"):
   config3_top100   (N = 1) the same store and batch at top-100 = BASELINE config 3 proper
   strong_scaling   BASELINE config 4 at every N, including N = 1: 100 M songs TOTAL row-sharded over the N GPUs,
                    batches of 8192 queries, top-100 ("scaling": "strong"; T_1 / (N T_N) is the efficiency)
+  all_pairs_1M     BASELINE config 5 at every N: the top-10 neighbour table of 1 M songs, store replicated, queries sharded
   roofline_hbm_regime, reference_gpu_path (N = 1): the HBM-bound regime of the same kernels, and the
                    reference's own cuBLAS path rebuilt for sm_100a (oracle/_ref/libref_gpu.so) on BASELINE config 2
 
@@ -436,6 +437,40 @@ def reference_gpu_path(job: Job) -> dict:
         return {"error": str(exc)}
 
 
+def all_pairs_case(job: Job) -> dict:
+    """BASELINE config 5: the top-10 neighbour table of 1 M songs (10^12 scored pairs).  The store is replicated, rank r
+    owns the query songs [r * ceil(N/G), ...), no exchange until the final gather of the table.  Wall clock
+    per rank around the host-output call plus the gather, max over ranks; a sample of rank 0's rows against the oracle."""
+    try:
+        from oracle_lib import Oracle
+        from spotify_recommender_b200 import synth
+        from spotify_recommender_b200.sharded import QueryShardedAllPairs
+        n, k = 1_000_000, 10
+        f = synth.features(n)
+        ap = QueryShardedAllPairs(job.eng, device=job.dev)
+        ap.load_replicated(f)
+        lo, hi = ap.local_range()
+        job.eng.all_pairs_topk(lo, min(hi, lo + 16384), k)  # warm-up
+        job.barrier()
+        t0 = time.perf_counter()
+        li, ls = ap.local_topk(k)
+        t_local = time.perf_counter() - t0
+        gi, gs = ap.gather_table(li, ls)
+        dt = job.max_over_ranks(time.perf_counter() - t0)
+        t_local = job.max_over_ranks(t_local)
+        sel = np.unique(np.linspace(0, n - 1, PARITY_QUERIES).astype(np.int64)).astype(np.int32)
+        wi, ws = Oracle().query_index(f, sel, k, threads=max(1, host_cores() // max(1, job.world)))
+        bad = int(((gi[sel] != wi).any(axis=1) | (gs[sel].view(np.uint32) != ws.view(np.uint32)).any(axis=1)).sum())
+        ok = bool((gi >= 0).all() and (gi != np.arange(n)[:, None]).all())
+        return {"workload": f"BASELINE config 5: all-pairs top-{k} over {n} songs ({n}^2 scored pairs), store replicated, queries sharded "
+                            f"over {job.world} GPU(s), host table out", "scaling": "strong", "n_gpus": job.world, "seconds": dt,
+                "seconds_local_topk": t_local, "value": float(n) * n / dt, "unit": "song-pairs/s",
+                "roofline_frac_fp32": FLOP_PER_PAIR * float(n) * n / max(1, job.world) / t_local / 1e12 / (job.sm_count * 128 * 2 * 1.965e9 / 1e12),
+                "parity_check": {"queries": int(sel.size), "mismatches": bad, "top_k": k, "songs": n, "table_complete": ok}}
+    except Exception as exc:
+        return {"error": str(exc)}
+
+
 def run_ours(args) -> None:
     global BATCH, TOPK
     if args.batch:
@@ -491,6 +526,8 @@ def run_ours(args) -> None:
                   "parity_check": c4["parity_check"], "gpu_launches": c4["gpu_launches"],
                   "efficiency_is": "T(n_gpus = 1) / (n_gpus x T(n_gpus)) over the ms_per_step of this key at each N"}
 
+    allpairs = all_pairs_case(job) if not args.quick and not args.songs_total else None
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": main["value"], "unit": "song-pairs/s", "n_gpus": world, "steps": args.steps,
@@ -510,6 +547,7 @@ def run_ours(args) -> None:
             "parity_check": main["parity_check"],
             "config3_top100": top100,
             "strong_scaling": strong,
+            "all_pairs_1M": allpairs,
             "roofline_hbm_regime": hbm,
             "reference_gpu_path": refgpu,
             "cpu_baseline": cpu,

@@ -143,6 +143,9 @@ int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k,
  *   "list_ws"   1 (default): the CTAs' top-k lists may live in an L2-resident workspace instead of shared
  *               memory when that keeps the query tile at 256 queries (used for 16 < k <= "list_ws_kmax"); 0: never
  *   "small_max" batches of at most this many queries take the TMA-staged small-batch kernel shape
+ *   "graphs"    1 (default): single-group passes of up to 256 queries are captured once per (buffers, nq, k) as a
+ *               CUDA graph and replayed with one launch; 0: always launch kernel by kernel
+ *   "bound_blocks", "prefetch", "refresh_every", "mid_max", "list_ws_kmax": development knobs
  *   "bound_tiles" layout tiles (2048 songs each) sampled by the threshold bound pass (0 = auto: 48 for k <= 16, else 128)
  *   "trigger_at" a settle phase starts when some hit buffer holds this many ids (0 = cap / 4)
  *   "settle_at" ... and scores and merges every buffer holding at least this many (0 = cap / 32)
@@ -154,8 +157,8 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value);
 /* Counters since create()/reset (synchronises the engine's stream):
  * "kernel_launches", "queries", "filter_hits", "settles", "rescans", "refilters", "rescored",
  * "irregular_songs", "sm_count", "scan_grid", "scan_tile_songs", "device_bytes",
- * "variant" (the shape the last pass used), "qt", "lists_in_smem" (of the last pass), "bad_index"
- * (reads and clears the flag described above). */
+ * "variant" (the shape the last pass used), "qt", "lists_in_smem" (of the last pass), "graph_replays",
+ * "bad_index" (reads and clears the flag described above). */
 int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value);
 
 /* With "profile" on: total device milliseconds and launch count of one kernel

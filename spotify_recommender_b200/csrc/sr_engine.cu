@@ -127,7 +127,7 @@ struct sr_engine {
                             // than the register-loading shape by more than 2 %, so off by default)
     int refresh_every = 0;  // tiles between two looks at the thresholds other CTAs published (0: automatic)
     int bound_blocks = 0;   // disjoint sample blocks of the bound pass (0: 64 / 128 / 256 by k)
-    int prefetch = -1;      // L2 prefetch of the next song tile in the dynamic shape (-1: for groups of <= 640 queries)
+    int prefetch = 0;       // 1: L2 bulk prefetch of the next song tile in the dynamic register-loading shape (no measured gain)
     int bound_tiles = 0;    // layout tiles (of S x 256 songs) the bound pass samples (0: 48 for k <= 16, else 128)
     bool profile = false;
 
@@ -144,6 +144,23 @@ struct sr_engine {
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     int scan_grid = 0;
     int last_lists_in_smem = 1;
+
+    // Small single-group passes are replayed as CUDA graphs: prep + bound + scan + finalize captured once per
+    // (buffers, nq, k, shape) and launched with one call -- the reference's only real use is one query per call
+    // (main.cpp:71,82), where the four launches around an 80 us kernel are what a user waits for.
+    struct GraphKey {
+        const void *p[8];
+        int nq, K, stride, col;
+        bool operator<(const GraphKey &o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+    };
+    struct GraphEntry {
+        cudaGraphExec_t exec;
+        int launches;
+    };
+    std::map<GraphKey, GraphEntry> graphs;
+    int64_t epoch = 0, graphs_epoch = 0;   // any reallocation, store load or option change invalidates the cache
+    int use_graphs = 1;
+    int64_t graph_replays = 0;
 
     // counters
     int64_t launches = 0, queries = 0;
@@ -192,6 +209,7 @@ int ensure(sr_engine *e, DevBuf &b, size_t bytes)
     SR_CUDA(cudaMalloc(&b.p, want));
     b.cap = want;
     e->device_bytes += (int64_t)want;
+    ++e->epoch;
     return SR_OK;
 }
 
@@ -292,6 +310,7 @@ int alloc_store(sr_engine *e, int64_t n, int64_t id_base)
     e->n = n;
     e->n_pad = n_pad;
     e->id_base = (int32_t)id_base;
+    ++e->epoch;
     SR_CUDA(cudaMemsetAsync(e->d_raw + (size_t)n * kF, 0, (size_t)(n_pad - n) * kF * 4, e->stream));
     return SR_OK;
 }
@@ -440,6 +459,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     cudaEvent_t &ev = g_bank_event[e->device & 63];
     if (!ev) SR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     else SR_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    // everything the pass enqueues, on `st` -- directly, or into a stream capture (no event operations then)
+    auto enqueue = [&](cudaStream_t st, bool capturing) -> int {
     {
         // one kernel resets the pass's workspace, prepares the queries and -- for a single-group pass --
         // writes the normalised rows straight into the constant bank
@@ -492,7 +513,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         a.trigger_at = trigger_at_eff;
         a.gslot = (uint32_t *)e->gslot.p + (size_t)g0 * nslot;
         a.nslot = nslot;
-        a.prefetch = e->prefetch >= 0 ? e->prefetch : (gq <= 640 ? 1 : 0);
+        a.prefetch = e->prefetch > 0 ? 1 : 0;  // (measured three times, from 64 to 4096 queries per batch and at top-100: no change)
         a.ceil = out.ceil_in ? out.ceil_in + g0 : nullptr;
         a.pool = (uint64_t *)e->pool.p + (size_t)g0 * slab; a.pool_cnt = (int32_t *)e->pool_cnt.p + g0;
         a.segs = segs; a.slab = slab;
@@ -531,7 +552,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             Scope sc(e, st, kScan);
             SR_CUDA(vl->launch(a, ggrid, smem, st));
         }
-        SR_CUDA(cudaEventRecord(ev, st));
+        if (!capturing) SR_CUDA(cudaEventRecord(ev, st));
     }
     {
         FinalArgs f;
@@ -543,6 +564,51 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         Scope sc(e, st, kFinalize);
         finalize_kernel<256><<<nq, 256, 0, st>>>(f);
         SR_CUDA(cudaGetLastError());
+    }
+    return SR_OK;
+    };
+
+    const bool graphable = e->use_graphs && !e->profile && groups == 1 && nq <= 256;
+    if (!graphable) {
+        if ((rc = enqueue(st, false))) return rc;
+    } else {
+        if (e->graphs_epoch != e->epoch || e->graphs.size() > 64) {
+            for (auto &kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+            e->graphs.clear();
+            e->graphs_epoch = e->epoch;
+        }
+        sr_engine::GraphKey key;
+        memset(&key, 0, sizeof key);
+        const void *ptrs[8] = {d_qidx, d_qrows, d_excl, out.idx, out.score, out.keys, out.ceil_in, out.ceil_out};
+        memcpy(key.p, ptrs, sizeof ptrs);
+        key.nq = nq; key.K = K; key.stride = out.stride; key.col = out.col;
+        auto it = e->graphs.find(key);
+        if (it == e->graphs.end()) {
+            // captured on the engine's own stream (the caller's may be the legacy stream, which cannot capture);
+            // a capture only records, it does not run or wait for anything
+            const int64_t launches_before = e->launches;
+            SR_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue(e->stream, true);
+            cudaGraph_t g = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+            const int captured = (int)(e->launches - launches_before);
+            e->launches = launches_before;
+            if (rc || ce != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                return rc ? rc : fail(e, SR_ECUDA, "stream capture of a small pass failed: %s", cudaGetErrorString(ce));
+            }
+            cudaGraphExec_t ex = nullptr;
+            const cudaError_t ie = cudaGraphInstantiate(&ex, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) return fail(e, SR_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+            it = e->graphs.emplace(key, sr_engine::GraphEntry{ex, captured}).first;
+        } else {
+            ++e->graph_replays;
+        }
+        SR_CUDA(cudaGraphLaunch(it->second.exec, st));
+        e->launches += it->second.launches;
+        SR_CUDA(cudaEventRecord(ev, st));
     }
     e->queries += nq;
     return SR_OK;
@@ -694,6 +760,7 @@ void sr_engine_destroy(sr_engine *e)
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto &t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto &kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     DevBuf *bufs[] = {&e->qraw, &e->qn, &e->qhat, &e->excl, &e->gbest, &e->gbound, &e->gslot, &e->ctr, &e->pool_cnt, &e->pool, &e->minmax, &e->list_ws,
                       &e->out, &e->out2, &e->qin, &e->ceil};
@@ -970,6 +1037,7 @@ int sr_engine_all_pairs_topk(sr_engine *e, int64_t q_lo, int64_t q_hi, int k, in
 int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
 {
     if (!e || !key) return SR_EINVAL;
+    ++e->epoch;  // captured passes were planned under the old options
     if (!strcmp(key, "variant")) {
         if (value < -1 || value >= kNumVariants) return fail(e, SR_EINVAL, "variant must be -1 (auto) or in [0, %d)", kNumVariants);
         e->variant = (int)value;
@@ -1006,7 +1074,9 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
         if (value != 0 && (value < 2 || value > kLT)) return fail(e, SR_EINVAL, "bound_blocks must be 0 (auto) or in [2, %d]", kLT);
         e->bound_blocks = (int)value;
     } else if (!strcmp(key, "prefetch")) {
-        e->prefetch = value < 0 ? -1 : (value != 0);
+        e->prefetch = value != 0;
+    } else if (!strcmp(key, "graphs")) {
+        e->use_graphs = value != 0;
     } else if (!strcmp(key, "refresh_every")) {
         if (value < 0 || value > 64) return fail(e, SR_EINVAL, "refresh_every must be in [0, 64]");
         e->refresh_every = (int)value;
@@ -1064,6 +1134,7 @@ int sr_engine_get_stat(sr_engine *e, const char *key, int64_t *value)
     else if (!strcmp(key, "variant")) *value = e->last_variant;
     else if (!strcmp(key, "qt")) *value = e->qt_opt;
     else if (!strcmp(key, "lists_in_smem")) *value = e->last_lists_in_smem;
+    else if (!strcmp(key, "graph_replays")) *value = e->graph_replays;
     else if (!strcmp(key, "bad_index")) {  // reads (and clears) the sticky flag the device-pointer calls leave behind
         SR_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, 4, cudaMemcpyDeviceToHost, e->stream));
         SR_CUDA(cudaStreamSynchronize(e->stream));

@@ -139,11 +139,11 @@ class QueryShardedAllPairs:
             return np.empty((0, k), np.int32), np.empty((0, k), np.float32)
         return self.engine.all_pairs_topk(lo, hi, k)
 
-    def all_pairs_topk(self, k: int):
-        """(idx[N,k] int32, score[N,k] f32) host arrays, identical on every rank."""
-        li, ls = self.local_topk(k)
+    def gather_table(self, li: np.ndarray, ls: np.ndarray):
+        """The one exchange of the path: every rank's slice -> the whole N x k table on every rank."""
         if self.world == 1:
             return li, ls
+        k = li.shape[1]
         per = -(-self.n // self.world)
         pad_i = torch.full((per, k), -1, dtype=torch.int32)
         pad_s = torch.zeros((per, k), dtype=torch.float32)
@@ -155,3 +155,8 @@ class QueryShardedAllPairs:
         dist.all_gather_into_tensor(all_i, d_i, group=self.group)
         dist.all_gather_into_tensor(all_s, d_s, group=self.group)
         return all_i[:self.n].cpu().numpy(), all_s[:self.n].cpu().numpy()
+
+    def all_pairs_topk(self, k: int):
+        """(idx[N,k] int32, score[N,k] f32) host arrays, identical on every rank."""
+        li, ls = self.local_topk(k)
+        return self.gather_table(li, ls)

@@ -348,3 +348,33 @@ def test_headline_size_parity(eng, oracle, data, k):
     assert gi.min() >= 0 and gi.max() < n and np.all(gi != q[:, None])
     ds = np.diff(gs.astype(np.float64), axis=1)
     assert np.all(ds <= 0) and np.all(np.diff(gi.astype(np.int64), axis=1)[ds == 0] > 0)
+
+
+def test_small_passes_replayed_as_cuda_graphs(eng, oracle):
+    """Single-query and small-batch calls go through one captured graph per (buffers, nq, k): the same buffers with
+    new query ids replay it, a reloaded store or a changed option re-captures, and every answer equals the oracle."""
+    import torch
+    n, k = 300_000, 10
+    f = synth.features(n)
+    eng.load_features(f)
+    before = eng.stat("graph_replays")
+    for q in (5, 77_777, 299_999, 5):                      # host path: the engine's own staging buffers are the graph's
+        assert_exact(eng.query_by_index([q], k), oracle.query_index(f, [q], k))
+    assert eng.stat("graph_replays") >= before + 3
+    dq = torch.zeros(8, dtype=torch.int32, device="cuda")
+    oi = torch.empty((8, k), dtype=torch.int32, device="cuda")
+    os_ = torch.empty((8, k), dtype=torch.float32, device="cuda")
+    for rep in range(4):                                   # device path on torch's (legacy default) stream
+        q = synth.query_indices(8, n) + rep * 1000
+        dq.copy_(torch.from_numpy(q))
+        eng.query_by_index_dev(dq, 8, k, oi, os_, stream=0)
+        torch.cuda.synchronize()
+        assert_exact((oi.cpu().numpy(), os_.cpu().numpy()), oracle.query_index(f, q, k))
+    f2 = synth.uniform(200_000)
+    eng.load_features(f2)                                  # new store: the cached graphs are dropped
+    assert_exact(eng.query_by_index([5], k), oracle.query_index(f2, [5], k))
+    eng.set_option("graphs", 0)
+    r0 = eng.stat("graph_replays")
+    assert_exact(eng.query_by_index([6], k), oracle.query_index(f2, [6], k))
+    assert_exact(eng.query_by_index([7], k), oracle.query_index(f2, [7], k))
+    assert eng.stat("graph_replays") == r0
