@@ -12,7 +12,11 @@
  *     isGPUEnabled() == isInitialized();
  *   - exact ties are ordered by lower song index (the reference's order on ties is
  *     an artefact of its heap, Recommender.cu:293-315);
- *   - topN <= 0 returns {} (the reference dereferences an empty heap);
+ *   - topN <= 0 returns {} (the reference dereferences an empty heap); any other topN yields min(topN, N - 1)
+ *     results like the reference (Recommender.cu:300-315);
+ *   - more than one GPU: a store of >= 20 M songs, or SR_DEVICES="0,1,..." in the environment, row-shards the songs
+ *     over several devices inside this process (the reference is hard-wired to device 0, Recommender.cu:124); the
+ *     results do not depend on the number of devices;
  *   - track-id and name lookups use indexes built once in initialize() but keep the
  *     reference's first-match rules (Recommender.cu:320-354).
  */

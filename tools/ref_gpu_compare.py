@@ -1,14 +1,24 @@
-"""BASELINE config 2: 1M songs x 12, batch of 1024 queries, top-10 -- this engine vs the
-reference's own cuBLAS SGEMV path rebuilt for sm_100a (oracle/_ref/libref_gpu.so: the
-unmodified Recommender.cu; its batch mode is 1024 sequential recommendByIndex calls)."""
-import sys, time, json
+"""This engine vs the reference's own cuBLAS SGEMV path rebuilt for sm_100a (oracle/_ref/libref_gpu.so: the unmodified
+Recommender.cu; its batch mode is sequential recommendByIndex calls), host buffers in and out, same box, same data.
+
+    python tools/ref_gpu_compare.py [songs] [queries] [reference_sample]
+
+BASELINE config 2 is 1e6 songs x 1024 queries; a 1e7 spot check times a few reference queries only."""
+import json
+import sys
+import time
+
 import numpy as np
+
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 from oracle_lib import Reference
 from spotify_recommender_b200 import synth
 from spotify_recommender_b200.engine import Engine
 
-n, nq, k = 1_000_000, 1024, 10
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
+nq = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+sample = int(sys.argv[3]) if len(sys.argv) > 3 else nq
+k = 10
 f = synth.features(n)
 q = synth.query_indices(nq, n)
 eng = Engine(0); eng.load_features(f)
@@ -16,13 +26,20 @@ for _ in range(3): gi, gs = eng.query_by_index(q, k)
 t0 = time.perf_counter()
 for _ in range(10): gi, gs = eng.query_by_index(q, k)
 t_ours = (time.perf_counter() - t0) / 10
+for _ in range(3): eng.query_by_index(q[:1], k)
+t0 = time.perf_counter()
+for i in range(50): eng.query_by_index(q[i:i + 1], k)
+t_one = (time.perf_counter() - t0) / 50
 ref = Reference(f, gpu=True)
 assert ref.gpu_enabled(), "reference fell back to its CPU path"
-ref.batch(q[:32], k)
+ref.batch(q[:8], k)
 t0 = time.perf_counter()
-ri = ref.batch(q, k)
-t_ref = time.perf_counter() - t0
-same = int((ri == gi).all(axis=1).sum())
-print(json.dumps({"config": "1M songs x 12, 1024 queries, top-10, host buffers in and out",
-                  "ours_ms_per_batch": t_ours * 1e3, "reference_cublas_path_ms_per_batch": t_ref * 1e3,
-                  "speedup": t_ref / t_ours, "identical_ordered_lists": f"{same}/{nq}"}))
+ri = ref.batch(q[:sample], k)
+t_ref = (time.perf_counter() - t0) / sample
+same = int((ri == gi[:sample]).all(axis=1).sum())
+print(json.dumps({"config": f"{n} songs x 12, {nq} queries, top-{k}, host buffers in and out",
+                  "ours_ms_per_batch": t_ours * 1e3, "ours_ms_single_query_call": t_one * 1e3,
+                  "reference_cublas_path_ms_per_query": t_ref * 1e3,
+                  "reference_cublas_path_ms_per_batch": t_ref * 1e3 * nq, "reference_sample": sample,
+                  "speedup_per_batch": t_ref * nq / t_ours, "speedup_single_query": t_ref / t_one,
+                  "identical_ordered_lists": f"{same}/{sample}"}))
