@@ -109,10 +109,23 @@ int sr_engine_merge_topk_dev(sr_engine *e, const int32_t *d_idx, const float *d_
 /* The same local scoring with the result in the EXCHANGE FORMAT of the row-sharded path: one packed 64-bit key per
  * candidate (orderable score << 32 | ~id; 0 = none), nq x k, so that a step needs exactly one all-gather.
  * d_ceil is NULL or nq keys: only candidates ordered strictly after d_ceil[q] are admitted (how a list longer
- * than 1024 continues across shards).  1 <= k <= 1024. */
+ * than 1024 continues across shards).  d_blocks is NULL or the max-reduced block maxima of the SHARED bound
+ * pass below: the shard then starts from thresholds that bound the k-th best of the whole store, and its list
+ * may hold fewer than k keys (only those that can still make the merged top-k).  1 <= k <= 1024. */
 int sr_engine_query_keys_by_vector_dev(sr_engine *e, const float *d_qrows, const int32_t *d_exclude,
-                                       int nq, int k, const uint64_t *d_ceil, uint64_t *d_out_keys,
-                                       void *stream);
+                                       int nq, int k, const uint64_t *d_ceil, const float *d_blocks,
+                                       uint64_t *d_out_keys, void *stream);
+
+/* The threshold bound pass shared between the `shards` row shards of one store: this shard
+ * samples 1 / shards of the tiles a single store would and writes, per query, the best filter score of each of
+ * sr_engine_bound_block_count(k) disjoint blocks of its sample (nq x blocks floats, -inf = none).  The caller
+ * max-reduces the arrays of all shards element-wise (one all-reduce) and hands the result to
+ * sr_engine_query_keys_by_vector_dev.  Block b of every shard holds different songs, so the (k+1)-th largest
+ * reduced maximum bounds the store-wide k-th best: every shard scans with the whole store's threshold at an
+ * eighth of the sampling cost.  block_count is 0 when lists of k have no bound pass (k > 255). */
+int sr_engine_bound_block_count(sr_engine *e, int k);
+int sr_engine_bound_blocks_dev(sr_engine *e, const float *d_qrows, int nq, int k, int shards,
+                               float *d_blocks, void *stream);
 
 /* Merge of `parts` gathered key lists (parts x nq x k, as one NCCL all-gather of the buffers above delivers
  * them) into columns [col, col + k) of the nq x stride result rows; d_ceil_out (or NULL) receives each

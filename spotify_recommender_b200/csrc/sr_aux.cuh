@@ -338,6 +338,51 @@ __global__ void gather_rows_p2p_kernel(const float *const *raw, int64_t per, int
     o[0] = __ldcg(p); o[1] = __ldcg(p + 1); o[2] = __ldcg(p + 2);
 }
 
+// ---- the bound pass shared between row shards: exchange format and finish --------------------------
+// Block maxima leave the engine as floats (-inf = no song seen): max is what the shards' all-reduce computes.
+__global__ void blocks_to_float_kernel(const uint32_t *gmax, int64_t count, float *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = gmax[i] ? ord2f(gmax[i]) : -__int_as_float(0x7f800000);
+}
+
+// Single-process form of that all-reduce: out = element-wise max over the shards' arrays, read over peer access.
+__global__ void blocks_max_p2p_kernel(const float *const *parts, int nparts, int64_t count, float *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float m = __ldcg(parts[0] + i);
+    for (int p = 1; p < nparts; ++p) m = fmaxf(m, __ldcg(parts[p] + i));
+    out[i] = m;
+}
+
+// One warp per query: the (K+1)-th largest of the nblk max-reduced block maxima (each the best filter score of a
+// disjoint set of songs of the WHOLE store, at most one of them the query itself) bounds the store-wide K-th best.
+__global__ void __launch_bounds__(256) blocks_finish_kernel(const float *blocks, int nblk, int K, uint32_t *g_best, int nq)
+{
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float *row = blocks + (size_t)q * nblk;
+    uint32_t v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const float f = (r * 32 + lane < nblk) ? row[r * 32 + lane] : -__int_as_float(0x7f800000);
+        v[r] = (f == -__int_as_float(0x7f800000)) ? 0u : f2ord(f);
+    }
+    uint32_t kth = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = kth | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) c += (v[r] >= cand);
+        if ((int)__reduce_add_sync(0xffffffffu, (unsigned)c) >= K + 1) kth = cand;
+    }
+    if (lane == 0 && kth != 0u) {
+        const uint32_t o = f2ord(ord2f(kth) - kBoundSlack);
+        if (o > g_best[q]) g_best[q] = o;
+    }
+}
+
 // ---- row gather (multi-GPU query exchange) --------------------------------
 // out[i] = raw row of global id ids[i] when this store owns it, else zeros: summing the
 // outputs of all shards (one all-reduce) gives every rank the full query matrix.

@@ -149,7 +149,7 @@ struct sr_engine {
     // (buffers, nq, k, shape) and launched with one call -- the reference's only real use is one query per call
     // (main.cpp:71,82), where the four launches around an 80 us kernel are what a user waits for.
     struct GraphKey {
-        const void *p[8];
+        const void *p[10];
         int nq, K, stride, col;
         bool operator<(const GraphKey &o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
     };
@@ -329,7 +329,20 @@ struct PassOut {
     int stride = 0, col = 0;    // the pass fills columns [col, col + K)
     const uint64_t *ceil_in = nullptr;  // [nq] only keys below these are admitted (or null)
     uint64_t *ceil_out = nullptr;       // [nq] receives the K-th key of the pass (or null)
+    // The bound pass shared between the row shards of one store: every shard samples 1 / sample_div of
+    // what a single store would, the block maxima are max-reduced across the shards (one small all-reduce), and every
+    // shard starts from thresholds that bound the K-th best of the WHOLE store.
+    int sample_div = 1;
+    float *blocks_out = nullptr;        // non-null: bound pass only -- [nq][bound blocks] block maxima (float, -inf = empty)
+    const float *blocks_in = nullptr;   // non-null: the max-reduced maxima; no bound pass of its own
 };
+
+// blocks of the bound pass for lists of K (the same on every shard: it sizes the exchange)
+int bound_block_count(const sr_engine *e, int K)
+{
+    const int nblk = e->bound_blocks > 0 ? std::max(e->bound_blocks, K + 1) : (K < 16 ? 64 : (K < 64 ? 128 : 256));
+    return (e->bound && K + 1 <= nblk && nblk <= kLT) ? nblk : 0;
+}
 
 // One internal pass: nq <= e->batch queries, K <= kKMax, everything on device, stream-ordered.
 int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const int32_t *d_excl, int nq, int K,
@@ -423,10 +436,15 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     const int64_t full_tiles = e->n / TS;
     // disjoint blocks of sample songs: at least K + 1, and several times that where it is cheap, so that the
     // (K+1)-th largest block maximum comes close to the sample's exact K-th best
-    const int nblk = e->bound_blocks > 0 ? std::max(e->bound_blocks, K + 1) : (K < 16 ? 64 : (K < 64 ? 128 : 256));
-    // sample tiles: 48 (short lists) or 96 layout tiles on large stores, never more than ~6 % of the store
-    const int n_sample = (int)std::min<int64_t>({(int64_t)(e->bound_tiles > 0 ? e->bound_tiles : (K <= 16 ? 48 : 96)) / (v.threads / kLT), std::max<int64_t>(4, full_tiles / 16), full_tiles / 4});
-    const bool use_bound = e->bound && !out.ceil_in && K + 1 <= nblk && nblk <= kLT && n_sample >= 4 && (int64_t)n_sample * TS >= 16 * (int64_t)nblk;
+    const bool shared = out.blocks_out || out.blocks_in;
+    const int nblk = shared ? bound_block_count(e, K) : (e->bound_blocks > 0 ? std::max(e->bound_blocks, K + 1) : (K < 16 ? 64 : (K < 64 ? 128 : 256)));
+    if (shared && (nblk == 0 || out.ceil_in)) return fail(e, SR_EINVAL, "a shared bound pass needs k <= 255, the \"bound\" option on and no ceiling");
+    // sample tiles: 48 (short lists) or 96 layout tiles on large stores, never more than ~6 % of the store; a shard of
+    // a store that shares its bound pass samples its part of them (at least one tile, none at all if it has none)
+    const int64_t want_tiles = (int64_t)(e->bound_tiles > 0 ? e->bound_tiles : (K <= 16 ? 48 : 96)) / (v.threads / kLT);
+    const int n_sample = shared ? (int)std::min<int64_t>(std::max<int64_t>(1, (want_tiles + out.sample_div - 1) / std::max(1, out.sample_div)), full_tiles)
+                                : (int)std::min<int64_t>({want_tiles, std::max<int64_t>(4, full_tiles / 16), full_tiles / 4});
+    const bool use_bound = shared ? (out.blocks_out != nullptr) : (e->bound && !out.ceil_in && K + 1 <= nblk && nblk <= kLT && n_sample >= 4 && (int64_t)n_sample * TS >= 16 * (int64_t)nblk);
     const int bqt = std::max(1, std::min({qt, 64, (int)(48 * 1024 / (nblk * 4))}));  // the bound pass's own (finer) query tiles: the block maxima of a tile live in shared memory
     const int bnqt_max = (gsize + bqt - 1) / bqt;
 
@@ -484,7 +502,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     // threshold bootstrap: the bound pass (filter speed, per query group, below) when the store
     // has enough full tiles, else / additionally the exact sample
     int m = e->sample;
-    if (out.ceil_in) m = 0;
+    if (out.ceil_in || shared) m = 0;
     if (m < 0 && use_bound) m = 0;
     if (m < 0) m = std::min(kSortCap, std::max(1024, 2 * pow2_floor((int64_t)K * 32 - 1)));
     if (m > 0) {
@@ -498,6 +516,11 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             sample_threshold_kernel<256><<<nq, 256, 0, st>>>(s);
             SR_CUDA(cudaGetLastError());
         }
+    }
+    if (out.blocks_in) {
+        blocks_finish_kernel<<<(nq + 7) / 8, 256, 0, st>>>(out.blocks_in, nblk, K, (uint32_t *)e->gbest.p, nq);
+        SR_CUDA(cudaGetLastError());
+        ++e->launches;
     }
     int gi = 0;
     for (int g0 = 0; g0 < nq; g0 += gsize, ++gi) {
@@ -526,7 +549,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             SR_CUDA(cudaMemcpyToSymbolAsync(c_qhat, (const float *)e->qhat.p + (size_t)g0 * kF, (size_t)gq * kF * 4, 0,
                                             cudaMemcpyDeviceToDevice, st));
         }
-        if (use_bound) {
+        a.bound_finish = out.blocks_out ? 0 : 1;
+        if (use_bound && n_sample > 0) {
             ScanArgs b = a;
             b.qt = bqt;
             const int bnqt = (gq + b.qt - 1) / b.qt;
@@ -535,7 +559,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             Scope sc(e, st, kBound);
             SR_CUDA(v.bound(b, nblk, n_sample, (int)(full_tiles / n_sample), gmax, gctr + 2 * nqt, bgrid, (size_t)b.qt * nblk * 4, st));
         }
-        {
+        if (!out.blocks_out) {
             a.n_tiles = n_tiles;
             a.tile_stride = 1;
             const int64_t gunits = (int64_t)gnqt * n_tiles;
@@ -553,6 +577,13 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             SR_CUDA(vl->launch(a, ggrid, smem, st));
         }
         if (!capturing) SR_CUDA(cudaEventRecord(ev, st));
+    }
+    if (out.blocks_out) {  // bound pass only: hand the block maxima over as floats (what the all-reduce maximises)
+        const int64_t count = (int64_t)nq * nblk;
+        blocks_to_float_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>((const uint32_t *)e->gbound.p, count, out.blocks_out);
+        SR_CUDA(cudaGetLastError());
+        ++e->launches;
+        return SR_OK;
     }
     {
         FinalArgs f;
@@ -579,9 +610,9 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         }
         sr_engine::GraphKey key;
         memset(&key, 0, sizeof key);
-        const void *ptrs[8] = {d_qidx, d_qrows, d_excl, out.idx, out.score, out.keys, out.ceil_in, out.ceil_out};
+        const void *ptrs[10] = {d_qidx, d_qrows, d_excl, out.idx, out.score, out.keys, out.ceil_in, out.ceil_out, out.blocks_out, out.blocks_in};
         memcpy(key.p, ptrs, sizeof ptrs);
-        key.nq = nq; key.K = K; key.stride = out.stride; key.col = out.col;
+        key.nq = nq; key.K = K; key.stride = out.stride; key.col = out.col + (out.sample_div << 16);
         auto it = e->graphs.find(key);
         if (it == e->graphs.end()) {
             // captured on the engine's own stream (the caller's may be the legacy stream, which cannot capture);
@@ -610,7 +641,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         e->launches += it->second.launches;
         SR_CUDA(cudaEventRecord(ev, st));
     }
-    e->queries += nq;
+    if (!out.blocks_out) e->queries += nq;
     return SR_OK;
 }
 
@@ -635,9 +666,11 @@ int check_query_args(sr_engine *e, const void *q, int nq, int k, const void *out
 // results at a time, each pass admitting only keys below the last key of the pass before (the ceiling), so the
 // caller sees min(k, songs - 1) results per query like the reference (Recommender.cu:300-315).
 int run_device(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const int32_t *d_excl, int nq, int k,
-               int32_t *d_out_idx, float *d_out_score, uint64_t *d_out_keys, const uint64_t *d_ceil, cudaStream_t st)
+               int32_t *d_out_idx, float *d_out_score, uint64_t *d_out_keys, const uint64_t *d_ceil, cudaStream_t st,
+               const float *d_blocks = nullptr)
 {
     const int chunks = (k + kKMax - 1) / kKMax;
+    const int blk_stride = d_blocks ? bound_block_count(e, k) : 0;
     for (int done = 0; done < nq; done += e->batch) {
         const int cur = std::min(e->batch, nq - done);
         int rc;
@@ -650,6 +683,7 @@ int run_device(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const 
             o.keys = d_out_keys ? d_out_keys + (size_t)done * k : nullptr;
             o.ceil_in = c > 0 ? (const uint64_t *)e->ceil.p : (d_ceil ? d_ceil + done : nullptr);
             o.ceil_out = c + 1 < chunks ? (uint64_t *)e->ceil.p : nullptr;
+            o.blocks_in = d_blocks ? d_blocks + (size_t)done * blk_stride : nullptr;
             rc = run_pass(e, d_qidx ? d_qidx + done : nullptr, d_qrows ? d_qrows + (size_t)done * kF : nullptr,
                           d_excl ? d_excl + done : nullptr, cur, std::min(kKMax, k - c * kKMax), o, st);
             if (rc) return rc;
@@ -853,14 +887,39 @@ int sr_engine_query_by_vector_dev(sr_engine *e, const float *d_qrows, const int3
 }
 
 int sr_engine_query_keys_by_vector_dev(sr_engine *e, const float *d_qrows, const int32_t *d_exclude, int nq, int k,
-                                       const uint64_t *d_ceil, uint64_t *d_out_keys, void *stream)
+                                       const uint64_t *d_ceil, const float *d_blocks, uint64_t *d_out_keys, void *stream)
 {
     int rc = check_query_args(e, d_qrows, nq, k, d_out_keys);
     if (rc) return rc;
     if (k > kKMax) return fail(e, SR_EINVAL, "query_keys: k must be in [1, %d] (got %d); longer lists go %d at a time under a ceiling", kKMax, k, kKMax);
+    if (d_blocks && d_ceil) return fail(e, SR_EINVAL, "query_keys: shared block maxima do not apply under a ceiling");
     SR_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = pick_stream(e, stream);
-    return run_device(e, nullptr, d_qrows, d_exclude, nq, k, nullptr, nullptr, d_out_keys, d_ceil, st);
+    return run_device(e, nullptr, d_qrows, d_exclude, nq, k, nullptr, nullptr, d_out_keys, d_ceil, st, d_blocks);
+}
+
+int sr_engine_bound_block_count(sr_engine *e, int k)
+{
+    return (e && k >= 1 && k <= kKMax) ? bound_block_count(e, k) : 0;
+}
+
+int sr_engine_bound_blocks_dev(sr_engine *e, const float *d_qrows, int nq, int k, int shards, float *d_blocks, void *stream)
+{
+    int rc = check_query_args(e, d_qrows, nq, k, d_blocks);
+    if (rc) return rc;
+    const int nblk = k <= kKMax ? bound_block_count(e, k) : 0;
+    if (!nblk) return fail(e, SR_EINVAL, "bound_blocks: no bound pass for k = %d (sr_engine_bound_block_count() is 0)", k);
+    if (shards < 1) return fail(e, SR_EINVAL, "bound_blocks: shards must be positive");
+    SR_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = pick_stream(e, stream);
+    for (int done = 0; done < nq; done += e->batch) {
+        const int cur = std::min(e->batch, nq - done);
+        PassOut o;
+        o.sample_div = shards;
+        o.blocks_out = d_blocks + (size_t)done * nblk;
+        if ((rc = run_pass(e, nullptr, d_qrows + (size_t)done * kF, nullptr, cur, k, o, st))) return rc;
+    }
+    return SR_OK;
 }
 
 namespace {

@@ -86,6 +86,7 @@ struct ScanArgs {
                              // score (orderable) any CTA has found among the songs with that residue
     int nslot;               // >= K, multiple of 32
     int prefetch;            // DYN shapes: bulk-prefetch the next song tile into L2 while the current one is multiplied
+    int bound_finish;        // bound_kernel: 1 = fold the block maxima into g_best (0: they are exchanged between shards first)
     const uint64_t *ceil;    // null, or [nq] per-query ceiling keys: only keys BELOW the ceiling are admitted (pass p > 0 of a
                              // K > kKMax query continues below the last key of pass p - 1); offset like the other per-query arrays
     unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] refilters; [5..12] cycle counters (-DSR_SCAN_TIMING)
@@ -972,7 +973,7 @@ __global__ void __launch_bounds__(THREADS, MINB) bound_kernel(const ScanArgs a, 
             if (s_max[i] > __ldcg(gmax + (size_t)q0 * nblk + i)) atomicMax(gmax + (size_t)q0 * nblk + i, s_max[i]);
         __threadfence();
         __syncthreads();
-        if (tid == 0) s_last = (atomicAdd(done_ctr + qtile, j_end - j) + (j_end - j) == n_sample);
+        if (tid == 0) s_last = a.bound_finish && (atomicAdd(done_ctr + qtile, j_end - j) + (j_end - j) == n_sample);
         __syncthreads();
         if (s_last) {
             // every sample tile of this query tile is in: (K+1)-th largest block maximum per query, one warp

@@ -4,8 +4,10 @@
 //
 //   row-sharded store (north_star (4)): shard s owns rows [s * per, (s + 1) * per) and answers with global ids.
 //   Per batch and per shard, on the shard's own stream: the query rows are read from their owners' raw stores
-//   over NVLink peer access (no exchange step for the queries), the fused scan produces the shard's exact top-K
-//   as packed 64-bit keys; the root shard's merge kernel then reads the G key lists straight out of the shards'
+//   over NVLink peer access (no exchange step for the queries); the threshold bound pass is SHARED -- every shard
+//   samples 1/G of the tiles, the block maxima are max-reduced by a kernel that reads the other shards' arrays over
+//   peer access, every shard scans with thresholds that bound the K-th best of the whole store; the fused scan
+//   produces the shard's candidates as packed 64-bit keys; the root shard's merge kernel then reads the G key lists straight out of the shards'
 //   buffers over peer access -- gather and merge are ONE kernel, nothing is staged -- and the merged rows go to
 //   the host.  Cross-device ordering is by CUDA events only.  (The multi-PROCESS host, one rank per GPU under
 //   torchrun, exchanges the same keys with one NCCL all-gather: spotify_recommender_b200/sharded.py.)
@@ -32,6 +34,10 @@ struct sr_sharded {
         float *d_qrows = nullptr;      // [batch][12]
         uint64_t *d_keys = nullptr;    // [batch][kKMax-capped k] local top-K keys
         size_t keys_cap = 0;
+        float *d_blocks = nullptr;     // [batch][256] this shard's block maxima of the shared bound pass ...
+        float *d_blocks_max = nullptr; // ... and their maximum over all shards (read over peer access)
+        const float **d_block_ptrs = nullptr;  // [G] every shard's d_blocks, on this shard's device
+        cudaEvent_t ev_blocks = nullptr;       // this shard's block maxima are complete
         const float **d_raw_ptrs = nullptr;  // [G] raw stores of every shard (peer pointers), on this shard's device
         cudaEvent_t ev_keys = nullptr;       // this shard's keys of the current pass are complete
     };
@@ -83,7 +89,11 @@ void sharded_free_buffers(sr_sharded *s)
         if (h.d_qrows) cudaFree(h.d_qrows);
         if (h.d_keys) cudaFree(h.d_keys);
         if (h.d_raw_ptrs) cudaFree((void *)h.d_raw_ptrs);
+        if (h.d_blocks) cudaFree(h.d_blocks);
+        if (h.d_blocks_max) cudaFree(h.d_blocks_max);
+        if (h.d_block_ptrs) cudaFree((void *)h.d_block_ptrs);
         h.d_q = nullptr; h.d_qrows = nullptr; h.d_keys = nullptr; h.d_raw_ptrs = nullptr; h.keys_cap = 0;
+        h.d_blocks = h.d_blocks_max = nullptr; h.d_block_ptrs = nullptr;
     }
 }
 
@@ -171,7 +181,19 @@ int sr_sharded_create(sr_sharded **out, const int *devices, int n_devices)
         if ((err = cudaMalloc(&h.d_q, (size_t)s->batch * 4)) != cudaSuccess) break;
         if ((err = cudaMalloc(&h.d_qrows, (size_t)s->batch * kF * 4)) != cudaSuccess) break;
         if ((err = cudaMalloc((void **)&h.d_raw_ptrs, G * sizeof(void *))) != cudaSuccess) break;
+        if ((err = cudaMalloc(&h.d_blocks, (size_t)s->batch * kLT * 4)) != cudaSuccess) break;
+        if ((err = cudaMalloc(&h.d_blocks_max, (size_t)s->batch * kLT * 4)) != cudaSuccess) break;
+        if ((err = cudaMalloc((void **)&h.d_block_ptrs, G * sizeof(void *))) != cudaSuccess) break;
+        if ((err = cudaEventCreateWithFlags(&h.ev_blocks, cudaEventDisableTiming)) != cudaSuccess) break;
         err = cudaEventCreateWithFlags(&h.ev_keys, cudaEventDisableTiming);
+    }
+    if (err == cudaSuccess) {
+        std::vector<const float *> bp(G);
+        for (int g = 0; g < G; ++g) bp[g] = s->sh[g].d_blocks;
+        for (int g = 0; g < G && err == cudaSuccess; ++g) {
+            cudaSetDevice(dev[g]);
+            err = cudaMemcpy((void *)s->sh[g].d_block_ptrs, bp.data(), G * sizeof(void *), cudaMemcpyHostToDevice);
+        }
     }
     if (err == cudaSuccess) {
         cudaSetDevice(dev[0]);
@@ -196,8 +218,11 @@ void sr_sharded_destroy(sr_sharded *s)
         cudaDeviceSynchronize();
     }
     sharded_free_buffers(s);
-    for (size_t g = 0; g < s->sh.size(); ++g)
-        if (s->sh[g].ev_keys) { cudaSetDevice(s->dev[g]); cudaEventDestroy(s->sh[g].ev_keys); }
+    for (size_t g = 0; g < s->sh.size(); ++g) {
+        cudaSetDevice(s->dev[g]);
+        if (s->sh[g].ev_keys) cudaEventDestroy(s->sh[g].ev_keys);
+        if (s->sh[g].ev_blocks) cudaEventDestroy(s->sh[g].ev_blocks);
+    }
     if (!s->dev.empty()) cudaSetDevice(s->dev[0]);
     if (s->d_part_ptrs) cudaFree((void *)s->d_part_ptrs);
     if (s->d_ceil) cudaFree(s->d_ceil);
@@ -297,6 +322,10 @@ int sr_sharded_query_by_index(sr_sharded *s, const int32_t *qidx, int nq, int k,
         float *d_os = out_score ? (float *)(s->d_out + (size_t)cur * k * 4) : nullptr;
         for (int c = 0; c < chunks; ++c) {
             const int kc = std::min(kKMax, k - c * kKMax);
+            // the bound pass is shared between the shards (first pass of a list only: ceilings have none): every shard
+            // samples 1/G of the tiles, the block maxima are max-reduced over peer access, every shard scans with
+            // thresholds that bound the k-th best of the WHOLE store
+            const int nblk = (c == 0 && G > 1) ? sr_engine_bound_block_count(root, kc) : 0;
             for (int g = 0; g < G; ++g) {
                 sr_engine *e = s->eng[g];
                 sr_sharded::Shard &h = s->sh[g];
@@ -308,8 +337,25 @@ int sr_sharded_query_by_index(sr_sharded *s, const int32_t *qidx, int nq, int k,
                     SRS_CUDA(cudaGetLastError());
                     ++e->launches;
                 }
-                SRS_ENGINE(g, sr_engine_query_keys_by_vector_dev(e, h.d_qrows, h.d_q, cur, kc, c > 0 ? s->d_ceil : nullptr, h.d_keys,
-                                                                 SR_ENGINE_OWN_STREAM));
+                if (nblk) {
+                    SRS_ENGINE(g, sr_engine_bound_blocks_dev(e, h.d_qrows, cur, kc, G, h.d_blocks, SR_ENGINE_OWN_STREAM));
+                    SRS_CUDA(cudaEventRecord(h.ev_blocks, e->stream));
+                }
+            }
+            for (int g = 0; g < G; ++g) {
+                sr_engine *e = s->eng[g];
+                sr_sharded::Shard &h = s->sh[g];
+                SRS_CUDA(cudaSetDevice(s->dev[g]));
+                if (nblk) {
+                    for (int o = 0; o < G; ++o)
+                        if (o != g) SRS_CUDA(cudaStreamWaitEvent(e->stream, s->sh[o].ev_blocks, 0));
+                    const int64_t count = (int64_t)cur * nblk;
+                    blocks_max_p2p_kernel<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>(h.d_block_ptrs, G, count, h.d_blocks_max);
+                    SRS_CUDA(cudaGetLastError());
+                    ++e->launches;
+                }
+                SRS_ENGINE(g, sr_engine_query_keys_by_vector_dev(e, h.d_qrows, h.d_q, cur, kc, c > 0 ? s->d_ceil : nullptr,
+                                                                 nblk ? h.d_blocks_max : nullptr, h.d_keys, SR_ENGINE_OWN_STREAM));
                 SRS_CUDA(cudaEventRecord(h.ev_keys, e->stream));
             }
             SRS_CUDA(cudaSetDevice(s->dev[0]));

@@ -25,7 +25,7 @@ EXPORTS = [
     "sr_engine_merge_topk_dev", "sr_engine_gather_rows_dev", "sr_engine_all_pairs_topk", "sr_engine_set_option", "sr_engine_get_stat",
     "sr_engine_get_timing", "sr_engine_variant_name", "sr_engine_measure_fp32", "sr_engine_selftest_div",
     "sr_engine_synchronize", "sr_engine_normalize_features", "sr_engine_normalize_features_dev", "sr_genre_ids",
-    "sr_engine_query_keys_by_vector_dev", "sr_engine_merge_keys_dev",
+    "sr_engine_query_keys_by_vector_dev", "sr_engine_merge_keys_dev", "sr_engine_bound_block_count", "sr_engine_bound_blocks_dev",
     "sr_sharded_create", "sr_sharded_destroy", "sr_sharded_last_error", "sr_sharded_load_features", "sr_sharded_song_count",
     "sr_sharded_shard_count", "sr_sharded_engine", "sr_sharded_query_by_index", "sr_sharded_all_pairs_topk",
 ]
@@ -78,7 +78,9 @@ def load_library() -> C.CDLL:
     L.sr_engine_normalize_features.argtypes = [vp, vp, vp, i64, i32, vp, vp]
     L.sr_engine_normalize_features_dev.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
     L.sr_genre_ids.argtypes = [C.POINTER(C.c_char_p), i64, i32, vp, C.POINTER(C.c_int32)]
-    L.sr_engine_query_keys_by_vector_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.sr_engine_query_keys_by_vector_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.sr_engine_bound_block_count.argtypes = [vp, i32]
+    L.sr_engine_bound_blocks_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.sr_engine_merge_keys_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]
     L.sr_sharded_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i32]
     L.sr_sharded_destroy.argtypes = [vp]
@@ -250,10 +252,20 @@ class Engine:
                                                     _ptr(d_out_idx), _ptr(d_out_score), _stream(stream)))
 
     def query_keys_by_vector_dev(self, d_qrows, d_exclude, nq: int, k: int, d_out_keys, d_ceil=None,
-                                 stream: int | None = None) -> None:
-        """Local top-k in the exchange format of the row-sharded path: nq x k packed 64-bit keys (0 = none)."""
+                                 stream: int | None = None, d_blocks=None) -> None:
+        """Local top-k in the exchange format of the row-sharded path: nq x k packed 64-bit keys (0 = none).
+        d_blocks: the max-reduced block maxima of the shared bound pass (bound_blocks_dev), or None."""
         self._check(self.L.sr_engine_query_keys_by_vector_dev(self.h, _ptr(d_qrows), _ptr(d_exclude), nq, k, _ptr(d_ceil),
-                                                              _ptr(d_out_keys), _stream(stream)))
+                                                              _ptr(d_blocks), _ptr(d_out_keys), _stream(stream)))
+
+    def bound_block_count(self, k: int) -> int:
+        """Blocks per query of the shared bound pass for lists of k (0: none -- k > 255)."""
+        return int(self.L.sr_engine_bound_block_count(self.h, k))
+
+    def bound_blocks_dev(self, d_qrows, nq: int, k: int, shards: int, d_blocks, stream: int | None = None) -> None:
+        """This shard's part of the bound pass shared between `shards` row shards: nq x bound_block_count(k) float
+        block maxima (-inf = none), to be max-reduced across the shards."""
+        self._check(self.L.sr_engine_bound_blocks_dev(self.h, _ptr(d_qrows), nq, k, shards, _ptr(d_blocks), _stream(stream)))
 
     def merge_keys_dev(self, d_keys, parts: int, nq: int, k: int, d_out_idx, d_out_score=None, stride: int = 0, col: int = 0,
                        d_ceil_out=None, stream: int | None = None) -> None:

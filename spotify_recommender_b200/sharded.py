@@ -21,8 +21,8 @@ def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
 
 
 class ShardedRecommender:
-    """`engine` needs load_features / gather_rows_dev / query_by_vector_dev / query_keys_by_vector_dev /
-    merge_keys_dev (spotify_recommender_b200.engine.Engine).  `group` is a
+    """`engine` needs load_features / gather_rows_dev / query_by_vector_dev / bound_block_count / bound_blocks_dev /
+    query_keys_by_vector_dev / merge_keys_dev (spotify_recommender_b200.engine.Engine).  `group` is a
     torch.distributed process group (NCCL on GPUs; the gloo tests drive the same
     host logic on CPU tensors with a checker-backed engine)."""
 
@@ -70,14 +70,24 @@ class ShardedRecommender:
             loc_s = self._scratch("loc_s", (nq, k), torch.float32)
             self.engine.query_by_vector_dev(qrows, d_qidx, nq, k, loc_i, loc_s, st)
             return loc_i, loc_s
-        # 2. local exact top-K over this shard as packed 64-bit keys (orderable score << 32 | ~global id),
+        # 2. the threshold bound pass, shared: every shard samples 1 / world of the tiles a single store would, the
+        #    block maxima are max-reduced (block b holds different songs on every shard), and every shard starts its
+        #    scan from thresholds that bound the K-th best of the WHOLE store -- an eighth of the sampling cost per
+        #    GPU at 8 GPUs, and no shard wastes time on candidates that cannot make the merged list
+        nblk = self.engine.bound_block_count(k)
+        blocks = None
+        if nblk:
+            blocks = self._scratch("blocks", (nq, nblk), torch.float32)
+            self.engine.bound_blocks_dev(qrows, nq, k, self.world, blocks, st)
+            dist.all_reduce(blocks, op=dist.ReduceOp.MAX, group=self.group)
+        # 3. local exact top-K over this shard as packed 64-bit keys (orderable score << 32 | ~global id),
         #    self excluded by global id
         keys = self._scratch("keys", (nq, k), torch.int64)
-        self.engine.query_keys_by_vector_dev(qrows, d_qidx, nq, k, keys, None, st)
-        # 3. the ONE exchange step: K keys per query from every shard
+        self.engine.query_keys_by_vector_dev(qrows, d_qidx, nq, k, keys, None, st, blocks)
+        # 4. the ONE exchange of results: K keys per query from every shard
         all_keys = self._scratch("all_keys", (self.world, nq, k), torch.int64)
         dist.all_gather_into_tensor(all_keys.view(self.world * nq, k), keys, group=self.group)
-        # 4. merge (every rank ends up with the final lists)
+        # 5. merge (every rank ends up with the final lists)
         out_i = self._scratch("out_i", (nq, k), torch.int32)
         out_s = self._scratch("out_s", (nq, k), torch.float32)
         self.engine.merge_keys_dev(all_keys, self.world, nq, k, out_i, out_s, 0, 0, None, st)

@@ -46,7 +46,18 @@ class CheckerEngine:
         d_out_score.copy_(torch.from_numpy(ms))
 
     # the exchange format of the row-sharded path: orderable(score + 0.0) << 32 | (0xFFFFFFFF - id), 0 = none
-    def query_keys_by_vector_dev(self, d_qrows, d_excl, nq, k, d_out_keys, d_ceil=None, stream=0):
+    def bound_block_count(self, k):
+        return 64
+
+    def bound_blocks_dev(self, d_qrows, nq, k, shards, d_blocks, stream=0):
+        # the checker has no bound pass: "no information" (-inf) is a valid contribution to the max-reduce
+        d_blocks.fill_(float("-inf"))
+        d_blocks[:, self.base % 64] = float(self.base)  # (a marker per shard, checked after the all-reduce)
+        self.shards = shards
+
+    def query_keys_by_vector_dev(self, d_qrows, d_excl, nq, k, d_out_keys, d_ceil=None, stream=0, d_blocks=None):
+        if d_blocks is not None:  # the reduced array carries every shard's marker
+            assert int(torch.isfinite(d_blocks[0]).sum()) == self.shards
         ex = d_excl.numpy().astype(np.int64) - self.base
         ex[(ex < 0) | (ex >= self.rows.shape[0])] = -1
         oi, os_ = self.o.query_rows(self.rows, d_qrows.numpy(), ex, k, id_base=self.base)

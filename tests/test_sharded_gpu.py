@@ -63,13 +63,27 @@ def test_row_shards_on_one_gpu_equal_single_store(oracle, G, data, n):
         all_keys = torch.zeros((G, nq, k), dtype=torch.int64, device="cuda")
         for g, e in enumerate(engines):
             e.query_keys_by_vector_dev(qrows, dq, nq, k, all_keys[g], None, stream=0)
+        local_keys = all_keys.clone()
+        # ... and with the bound pass shared between the shards (block maxima max-reduced as the all-reduce would):
+        # the shards' lists may be shorter, the merged rows are the same
+        nblk = engines[0].bound_block_count(k)
+        if nblk:
+            parts_b = torch.empty((G, nq, nblk), dtype=torch.float32, device="cuda")
+            for g, e in enumerate(engines):
+                e.bound_blocks_dev(qrows, nq, k, G, parts_b[g], stream=0)
+            blocks = parts_b.max(0).values.contiguous()
+            for g, e in enumerate(engines):
+                e.query_keys_by_vector_dev(qrows, dq, nq, k, all_keys[g], None, stream=0, d_blocks=blocks)
+            torch.cuda.synchronize()
+            assert int((all_keys != 0).sum()) <= int((local_keys != 0).sum())
         # 4. merge
         oi = torch.empty((nq, k), dtype=torch.int32, device="cuda")
         os_ = torch.empty((nq, k), dtype=torch.float32, device="cuda")
-        engines[0].merge_keys_dev(all_keys, G, nq, k, oi, os_, stream=0)
-        torch.cuda.synchronize()
         want = oracle.query_index(f, q, k, threads=8)
-        assert_exact((oi.cpu().numpy(), os_.cpu().numpy()), want)
+        for keys in (all_keys, local_keys):
+            engines[0].merge_keys_dev(keys, G, nq, k, oi, os_, stream=0)
+            torch.cuda.synchronize()
+            assert_exact((oi.cpu().numpy(), os_.cpu().numpy()), want)
         # the (idx, score) form of the merge gives the same rows
         loc_i = torch.empty((G, nq, k), dtype=torch.int32, device="cuda")
         loc_s = torch.empty((G, nq, k), dtype=torch.float32, device="cuda")
