@@ -83,6 +83,7 @@ const Variant kVariants[] = {
     SR_VARIANT_DYN(8, 512, 1),      // 5  large batches: dynamic tile claiming, tiles loaded straight into registers
     SR_VARIANT_DTMA(8, 512, 1),     // 6  mid-size batches, short lists: 64-query tiles, the next song tile staged by TMA meanwhile
     SR_VARIANT_TMA(8, 256, 2),      // 7  the static form of 4 (contiguous runs of units)
+    SR_VARIANT_DYN(8, 256, 2),      // 8  two 256-thread CTAs per SM loading straight into registers: one CTA's tile load hides behind the other's arithmetic
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 constexpr int kAutoSmall = 4, kAutoLarge = 5, kAutoMid = 6, kStaticLarge = 3, kAutoS = 8;
@@ -571,7 +572,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             a.visit_ctr = gctr + nqt;
             a.steal_max = steal_max;
             const Variant *vl = &v;
-            if (v.dynamic && gnqt > ggrid) vl = &kVariants[kStaticLarge];  // more query tiles than CTAs: static runs (same S, threads, smem)
+            if (v.dynamic && gnqt > ggrid) vl = &kVariants[v.threads == 512 ? kStaticLarge : 1];  // more query tiles than CTAs: static runs (same S, threads, smem)
             if (vl->dynamic) a.cpq = ggrid / gnqt;
             Scope sc(e, st, kScan);
             SR_CUDA(vl->launch(a, ggrid, smem, st));

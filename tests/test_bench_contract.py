@@ -40,11 +40,11 @@ def test_reference_arm_under_torchrun_only_rank0_prints():
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
 
 
-@pytest.mark.parametrize("name", ["r1_bench_n1.json", "r1_bench_n8.json"])
+@pytest.mark.parametrize("name", ["r1_bench_n1.json", "r1_bench_n8.json", "r2_bench_n1.json", "r2_bench_n2.json", "r2_bench_n4.json", "r2_bench_n8.json"])
 def test_recorded_gpu_line_has_every_contract_field(name):
     d = last_json_line(open(os.path.join(ROOT, "profiles", name)).read())
     assert BASE_KEYS - {"cpu_baseline"} <= set(d) and "impl" not in d
-    ref = last_json_line(open(os.path.join(ROOT, "profiles", "r1_bench_reference_arm.json")).read())
+    ref = last_json_line(open(os.path.join(ROOT, "profiles", name[:2] + "_bench_reference_arm.json")).read())
     assert d["metric"] == ref["metric"] and d["unit"] == ref["unit"]
     assert d["gpu_launches"] > 0 and d["steps"] >= 1 and d["warmup"] >= 3 and d["vs_baseline"] is None
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] <= d["value"] * 1.01
@@ -57,3 +57,22 @@ def test_recorded_gpu_line_has_every_contract_field(name):
     if d["n_gpus"] == 1:
         cb = d["cpu_baseline"]
         assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+def test_round2_lines_carry_parity_and_the_strong_scaling_record(n):
+    """Round 2: every case of the line ends with an oracle check of 32 sampled queries (0 mismatches), config 4 is
+    measured as a strong-scaling record at every N (100 M songs total), config 5 with sharded queries."""
+    d = last_json_line(open(os.path.join(ROOT, "profiles", f"r2_bench_n{n}.json")).read())
+    assert d["n_gpus"] == n and d["scaling"] == "weak"
+    assert d["parity_check"]["queries"] >= 32 and d["parity_check"]["mismatches"] == 0
+    st = d["strong_scaling"]
+    assert st["scaling"] == "strong" and st["n_gpus"] == n and st["parity_check"]["mismatches"] == 0
+    assert "100000000 songs TOTAL" in st["config"]["workload"] and st["ms_per_step"] > 0
+    ap = d["all_pairs_1M"]
+    assert ap["parity_check"]["mismatches"] == 0 and ap["parity_check"]["table_complete"] and ap["seconds"] > 0
+    if n == 1:
+        assert d["config3_top100"]["parity_check"]["mismatches"] == 0
+        assert d["roofline"]["traffic_source"].startswith("stored")
+        cases = {c["queries"]: c for c in d["roofline_hbm_regime"]["cases"]}
+        assert cases[1]["frac_call"] >= 0.75 and cases[1]["frac_scan_kernel"] >= 0.9
