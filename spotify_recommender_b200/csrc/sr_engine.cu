@@ -81,12 +81,13 @@ const Variant kVariants[] = {
     SR_VARIANT(8, 512, 1, true),    // 3  static runs of units (fallback of 5 when query tiles outnumber CTAs)
     SR_VARIANT_DTMA(8, 256, 2),     // 4  small batches (HBM-bound): TMA-staged tiles, dynamic tile claiming
     SR_VARIANT_DYN(8, 512, 1),      // 5  large batches: dynamic tile claiming, tiles loaded straight into registers
-    SR_VARIANT_DTMA(8, 512, 1),     // 6  mid-size batches, short lists: 64-query tiles, the next song tile staged by TMA meanwhile
+    SR_VARIANT_DTMA(8, 512, 1),     // 6  64-query tiles, the next song tile staged by TMA meanwhile (an experiment kept for reference: +2 % at
+                                    //    64 queries, slower above -- copying 196 KB out of shared memory costs what the hidden load saves)
     SR_VARIANT_TMA(8, 256, 2),      // 7  the static form of 4 (contiguous runs of units)
-    SR_VARIANT_DYN(8, 256, 2),      // 8  two 256-thread CTAs per SM loading straight into registers: one CTA's tile load hides behind the other's arithmetic
+    SR_VARIANT_DYN(8, 256, 2),      // 8  mid-size batches, short lists: two 256-thread CTAs per SM loading straight into registers
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-constexpr int kAutoSmall = 4, kAutoLarge = 5, kAutoMid = 6, kStaticLarge = 3, kAutoS = 8;
+constexpr int kAutoSmall = 4, kAutoLarge = 5, kAutoMid = 8, kStaticLarge = 3, kAutoS = 8;
 
 enum KernelId { kPrep = 0, kSample, kScan, kFinalize, kMerge, kBound, kNumKernels };
 const char *const kKernelNames[kNumKernels] = {"prep", "sample", "scan", "finalize", "merge", "bound"};
@@ -124,8 +125,8 @@ struct sr_engine {
     int list_ws_opt = 1;    // allow the CTAs' lists in an L2-resident workspace when that keeps the query tile at full size
     int list_ws_kmax = 72;  // ... for k up to this
     int small_max = 32;     // batches of at most this many queries take the TMA-staged small-batch shape
-    int mid_max = 0;        // ... and up to this many (k <= 16) the TMA-staged 64-query-tile shape (measured: never better
-                            // than the register-loading shape by more than 2 %, so off by default)
+    int mid_max = 192;      // ... and up to this many (k <= 16) two dynamic 256-thread CTAs per SM (measured against the
+                            // one-CTA shape: +10 % at 40 queries, +7 % at 64, +4 % at 128, -1 % at 256)
     int refresh_every = 0;  // tiles between two looks at the thresholds other CTAs published (0: automatic)
     int bound_blocks = 0;   // disjoint sample blocks of the bound pass (0: 64 / 128 / 256 by k)
     int prefetch = 0;       // 1: L2 bulk prefetch of the next song tile in the dynamic register-loading shape (no measured gain)
@@ -352,8 +353,8 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     // small batches are HBM-bound: two 256-thread CTAs per SM, song tiles staged through shared
     // memory by TMA one tile ahead; large batches are FP32-bound: one 512-thread CTA, bigger
     // tiles, shared memory spent on 256 queries' lists and hit buffers
-    // mid-size batches with short lists: the dynamic shape with 64-query tiles, whose song tiles (now a quarter of
-    // the arithmetic per load) are staged through shared memory by TMA while the previous tile is multiplied
+    // in between (short lists): two 256-thread CTAs per SM loading straight into registers -- with one query tile per
+    // launch a tile's load is 15-25 % of its time, and one CTA's load hides behind the other's arithmetic
     int vi = e->variant >= 0 ? e->variant : (nq <= e->small_max ? kAutoSmall : (nq <= e->mid_max && K <= 16 ? kAutoMid : kAutoLarge));
     const Variant *vp = nullptr;
     int TS = 0, n_tiles = 0, groups = 0, gsize = 0, qt_cap = 0, cap = 0;

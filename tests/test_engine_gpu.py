@@ -23,7 +23,7 @@ def eng():
     e.close()
 
 
-AUTO_SHAPES = (4, 5, 6)  # the shapes the engine picks by itself: TMA-staged small-batch, dynamic large-batch, TMA-staged mid-batch
+AUTO_SHAPES = (4, 5, 8)  # the shapes the engine picks by itself: TMA-staged small-batch, dynamic large-batch, two-CTA dynamic mid-batch
 
 
 def assert_exact(got, want):
