@@ -129,6 +129,7 @@ struct sr_engine {
                             // one-CTA shape: +10 % at 40 queries, +7 % at 64, +4 % at 128, -1 % at 256)
     int refresh_every = 0;  // tiles between two looks at the thresholds other CTAs published (0: automatic)
     int bound_blocks = 0;   // disjoint sample blocks of the bound pass (0: 64 / 128 / 256 by k)
+    int bound_cap_div = 16; // the bound pass samples at most 1 / this of the store's tiles
     int prefetch = 0;       // 1: L2 bulk prefetch of the next song tile in the dynamic register-loading shape (no measured gain)
     int bound_tiles = 0;    // layout tiles (of S x 256 songs) the bound pass samples (0: 48 for k <= 16, else 128)
     bool profile = false;
@@ -445,7 +446,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     // a store that shares its bound pass samples its part of them (at least one tile, none at all if it has none)
     const int64_t want_tiles = (int64_t)(e->bound_tiles > 0 ? e->bound_tiles : (K <= 16 ? 48 : 96)) / (v.threads / kLT);
     const int n_sample = shared ? (int)std::min<int64_t>(std::max<int64_t>(1, (want_tiles + out.sample_div - 1) / std::max(1, out.sample_div)), full_tiles)
-                                : (int)std::min<int64_t>({want_tiles, std::max<int64_t>(4, full_tiles / 16), full_tiles / 4});
+                                : (int)std::min<int64_t>({want_tiles, std::max<int64_t>(4, full_tiles / (e->bound_cap_div > 0 ? e->bound_cap_div : 16)), full_tiles / 4});
     const bool use_bound = shared ? (out.blocks_out != nullptr) : (e->bound && !out.ceil_in && K + 1 <= nblk && nblk <= kLT && n_sample >= 4 && (int64_t)n_sample * TS >= 16 * (int64_t)nblk);
     const int bqt = std::max(1, std::min({qt, 64, (int)(48 * 1024 / (nblk * 4))}));  // the bound pass's own (finer) query tiles: the block maxima of a tile live in shared memory
     const int bnqt_max = (gsize + bqt - 1) / bqt;
@@ -1131,6 +1132,9 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "list_ws_kmax")) {
         if (value < 0 || value > kKMax) return fail(e, SR_EINVAL, "list_ws_kmax must be in [0, %d]", kKMax);
         e->list_ws_kmax = (int)value;
+    } else if (!strcmp(key, "bound_cap_div")) {
+        if (value < 4 || value > 1024) return fail(e, SR_EINVAL, "bound_cap_div must be in [4, 1024]");
+        e->bound_cap_div = (int)value;
     } else if (!strcmp(key, "bound_blocks")) {
         if (value != 0 && (value < 2 || value > kLT)) return fail(e, SR_EINVAL, "bound_blocks must be 0 (auto) or in [2, %d]", kLT);
         e->bound_blocks = (int)value;
