@@ -85,6 +85,9 @@ const Variant kVariants[] = {
                                     //    64 queries, slower above -- copying 196 KB out of shared memory costs what the hidden load saves)
     SR_VARIANT_TMA(8, 256, 2),      // 7  the static form of 4 (contiguous runs of units)
     SR_VARIANT_DYN(8, 256, 2),      // 8  mid-size batches, short lists: two 256-thread CTAs per SM loading straight into registers
+    // (tried and dropped: SR_VARIANT_DTMA(4, 256, 3) -- 4 songs per thread, three CTAs per SM, 49 KB TMA stages, on the SAME
+    // store (an 8-song layout tile is two contiguous 4-song layout tiles).  At 85 registers ptxas keeps none of the FFMA2 query
+    // operands in uniform registers and the shape loses from 8 queries up: 16 queries 118 us against 99 us.)
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 constexpr int kAutoSmall = 4, kAutoLarge = 5, kAutoMid = 8, kStaticLarge = 3, kAutoS = 8;
@@ -279,10 +282,8 @@ int build_store(sr_engine *e)
     SR_CUDA(cudaMemsetAsync(e->d_irregular, 0, 8, e->stream));
     const int threads = 256;
     const int64_t blocks = (e->n_pad + threads - 1) / threads;
-    build_store_kernel<<<(unsigned)blocks, threads, 0, e->stream>>>(e->d_raw, e->n, e->n_pad, e->d_nf, e->d_hat,
-                                                                     e->variant >= 0 ? kVariants[e->variant].S : kAutoS,
-                                                                     e->d_irregular);
-    e->hat_S = e->variant >= 0 ? kVariants[e->variant].S : kAutoS;
+    build_store_kernel<<<(unsigned)blocks, threads, 0, e->stream>>>(e->d_raw, e->n, e->n_pad, e->d_nf, e->d_hat, kAutoS, e->d_irregular);
+    e->hat_S = kAutoS;
     SR_CUDA(cudaGetLastError());
     ++e->launches;
     unsigned long long irr = 0;
@@ -444,7 +445,13 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     if (shared && (nblk == 0 || out.ceil_in)) return fail(e, SR_EINVAL, "a shared bound pass needs k <= 255, the \"bound\" option on and no ceiling");
     // sample tiles: 48 (short lists) or 96 layout tiles on large stores, never more than ~6 % of the store; a shard of
     // a store that shares its bound pass samples its part of them (at least one tile, none at all if it has none)
-    const int64_t want_tiles = (int64_t)(e->bound_tiles > 0 ? e->bound_tiles : (K <= 16 ? 48 : 96)) / (v.threads / kLT);
+    // (small and mid-size batches: the pass is latency-bound there, so one tile per SM costs what 48 do and starts the scan
+    // with a third of the filter hits -- 16 queries over 10 M songs: 950 -> 317 hits per query, scan 104 -> 98.5 us; 64
+    // queries: 1123 -> 330, call 344 -> 317 us)
+    const bool few = nq <= std::max(e->small_max, e->mid_max) && K <= 16;
+    // (up to ~640 queries one or two query tiles are shared by all the CTAs, each with a list of its own: a four times larger
+    // sample -- 4 % of the scan's work -- halves the hits twice over and pays: 256 / 512 queries 1.095 / 2.104 -> 1.071 / 2.060 ms)
+    const int64_t want_tiles = (int64_t)(e->bound_tiles > 0 ? e->bound_tiles : (few ? std::max(48, e->sm_count) : (K <= 16 ? (nq <= 640 ? 192 : 48) : 96))) * (kAutoS / v.S) / (v.threads / kLT);
     const int n_sample = shared ? (int)std::min<int64_t>(std::max<int64_t>(1, (want_tiles + out.sample_div - 1) / std::max(1, out.sample_div)), full_tiles)
                                 : (int)std::min<int64_t>({want_tiles, std::max<int64_t>(4, full_tiles / (e->bound_cap_div > 0 ? e->bound_cap_div : 16)), full_tiles / 4});
     const bool use_bound = shared ? (out.blocks_out != nullptr) : (e->bound && !out.ceil_in && K + 1 <= nblk && nblk <= kLT && n_sample >= 4 && (int64_t)n_sample * TS >= 16 * (int64_t)nblk);
@@ -1103,7 +1110,7 @@ int sr_engine_set_option(sr_engine *e, const char *key, int64_t value)
     if (!strcmp(key, "variant")) {
         if (value < -1 || value >= kNumVariants) return fail(e, SR_EINVAL, "variant must be -1 (auto) or in [0, %d)", kNumVariants);
         e->variant = (int)value;
-        if (e->d_raw && e->hat_S != (e->variant >= 0 ? kVariants[e->variant].S : kAutoS)) {  // the normalised store is laid out per S
+        if (e->d_raw && e->hat_S != kAutoS) {  // (every shape of the table reads the 8-song layout: a 4-song tile is half of one)
             SR_CUDA(cudaSetDevice(e->device));
             SR_CUDA(cudaStreamSynchronize(e->stream));
             int rc = build_store(e);
