@@ -29,7 +29,7 @@ typedef cudaError_t (*ScanOcc)(int *ctas_per_sm, size_t smem);
 typedef cudaError_t (*BoundLaunch)(const ScanArgs &, int nblk, int n_sample, int stride, uint32_t *gmax, int *done_ctr, int grid,
                                    size_t smem, cudaStream_t st);
 
-template <int S, int T, int M, bool D, bool G, bool Y>
+template <int S, int T, int M, bool D, int G, bool Y>
 cudaError_t launch_scan(const ScanArgs &a, int grid, size_t smem, cudaStream_t st)
 {
     auto k = scan_kernel<S, T, M, D, G, Y>;
@@ -38,7 +38,7 @@ cudaError_t launch_scan(const ScanArgs &a, int grid, size_t smem, cudaStream_t s
     k<<<grid, T, smem, st>>>(a);
     return cudaGetLastError();
 }
-template <int S, int T, int M, bool D, bool G, bool Y>
+template <int S, int T, int M, bool D, int G, bool Y>
 cudaError_t occ_scan(int *ctas, size_t smem)
 {
     auto k = scan_kernel<S, T, M, D, G, Y>;
@@ -60,20 +60,25 @@ cudaError_t launch_bound(const ScanArgs &a, int nblk, int n_sample, int stride, 
 
 struct Variant {
     const char *name;
-    int S, threads, ctas;
-    bool staged, dynamic;
+    int S, threads, ctas;  // ctas: the kernel's __launch_bounds__ minimum (its register cap)
+    int nbuf;              // TMA staging buffers per CTA (0: tiles are loaded straight into registers)
+    bool dynamic;
+    bool staged() const { return nbuf > 0; }
+    int smem_ctas() const { return nbuf == 2 ? 1 : ctas; }  // CTAs per SM the shared-memory budget is shared by
     ScanLaunch launch;
     ScanOcc occ;
     BoundLaunch bound;
 };
 #define SR_VARIANT(S, T, M, D) \
-    {"S" #S "xT" #T "x" #M "-" #D, S, T, M, false, false, launch_scan<S, T, M, D, false, false>, occ_scan<S, T, M, D, false, false>, launch_bound<S, T, M>}
+    {"S" #S "xT" #T "x" #M "-" #D, S, T, M, 0, false, launch_scan<S, T, M, D, 0, false>, occ_scan<S, T, M, D, 0, false>, launch_bound<S, T, M>}
 #define SR_VARIANT_TMA(S, T, M) \
-    {"S" #S "xT" #T "x" #M "-tma", S, T, M, true, false, launch_scan<S, T, M, true, true, false>, occ_scan<S, T, M, true, true, false>, launch_bound<S, T, M>}
+    {"S" #S "xT" #T "x" #M "-tma", S, T, M, 1, false, launch_scan<S, T, M, true, 1, false>, occ_scan<S, T, M, true, 1, false>, launch_bound<S, T, M>}
 #define SR_VARIANT_DYN(S, T, M) \
-    {"S" #S "xT" #T "x" #M "-dyn", S, T, M, false, true, launch_scan<S, T, M, true, false, true>, occ_scan<S, T, M, true, false, true>, launch_bound<S, T, M>}
+    {"S" #S "xT" #T "x" #M "-dyn", S, T, M, 0, true, launch_scan<S, T, M, true, 0, true>, occ_scan<S, T, M, true, 0, true>, launch_bound<S, T, M>}
 #define SR_VARIANT_DTMA(S, T, M) \
-    {"S" #S "xT" #T "x" #M "-dyn-tma", S, T, M, true, true, launch_scan<S, T, M, true, true, true>, occ_scan<S, T, M, true, true, true>, launch_bound<S, T, M>}
+    {"S" #S "xT" #T "x" #M "-dyn-tma", S, T, M, 1, true, launch_scan<S, T, M, true, 1, true>, occ_scan<S, T, M, true, 1, true>, launch_bound<S, T, M>}
+#define SR_VARIANT_DTMA2(S, T, M) \
+    {"S" #S "xT" #T "x1-dyn-tma2", S, T, M, 2, true, launch_scan<S, T, M, true, 2, true>, occ_scan<S, T, M, true, 2, true>, launch_bound<S, T, M>}
 const Variant kVariants[] = {
     SR_VARIANT(8, 256, 2, false),   // 0  plain hit branch in the loop
     SR_VARIANT(8, 256, 2, true),    // 1  branch-free loop, deferred hits
@@ -85,6 +90,7 @@ const Variant kVariants[] = {
                                     //    64 queries, slower above -- copying 196 KB out of shared memory costs what the hidden load saves)
     SR_VARIANT_TMA(8, 256, 2),      // 7  the static form of 4 (contiguous runs of units)
     SR_VARIANT_DYN(8, 256, 2),      // 8  mid-size batches, short lists: two 256-thread CTAs per SM loading straight into registers
+    SR_VARIANT_DTMA2(8, 256, 2),    // 9  one 256-thread CTA per SM with TWO TMA staging buffers (a copy in flight at every moment)
     // (tried and dropped: SR_VARIANT_DTMA(4, 256, 3) -- 4 songs per thread, three CTAs per SM, 49 KB TMA stages, on the SAME
     // store (an 8-song layout tile is two contiguous 4-song layout tiles).  At 85 registers ptxas keeps none of the FFMA2 query
     // operands in uniform registers and the shape loses from 8 queries up: 16 queries 118 us against 99 us.)
@@ -368,7 +374,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             vi = kAutoLarge;
         }
         vp = &kVariants[vi];
-        if (vp->staged && vp->dynamic && (nq + std::min(e->qt_opt, kQTMax) - 1) / std::min(e->qt_opt, kQTMax) > e->sm_count * vp->ctas) {
+        if (vp->staged() && vp->dynamic && (nq + std::min(e->qt_opt, kQTMax) - 1) / std::min(e->qt_opt, kQTMax) > e->sm_count * vp->smem_ctas()) {
             vi = kAutoLarge;  // more query tiles than CTAs (only with a tiny "qt" option): the shape with a static fallback
             vp = &kVariants[vi];
         }
@@ -381,9 +387,9 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
         // the CTA's exact top-K lists (qt x K keys).  Large qt amortises the per-tile costs; cap of a
         // few K lets an overflowing buffer alone lift the threshold far enough for the re-filter
         // round to converge.  First combination that fits wins.
-        stage_bytes = vp->staged ? (size_t)TS * kF * 4 : 0;
-        const size_t smem_budget = vp->staged && vp->ctas == 1 ? (size_t)230000 : (size_t)216 * 1024 / vp->ctas;
-        const int qt_max = std::max(1, std::min({e->qt_opt, kQTMax, vp->staged && vp->ctas == 1 ? 64 : kQTMax}));
+        stage_bytes = (size_t)vp->nbuf * TS * kF * 4;
+        const size_t smem_budget = vp->staged() && vp->smem_ctas() == 1 ? (size_t)230000 : (size_t)216 * 1024 / vp->smem_ctas();
+        const int qt_max = std::max(1, std::min({e->qt_opt, kQTMax, vp->staged() && vp->smem_ctas() == 1 ? 64 : kQTMax}));
         const int kk = std::max(K, 32);
         for (int qtry = qt_max; qtry >= 1 && !qt_cap; qtry = (qtry > 8 ? qtry / 2 : qtry - 1)) {
             const int caps[4] = {e->hit_cap > 0 ? e->hit_cap : std::max(128, 4 * kk), std::max(128, 2 * kk),
@@ -393,7 +399,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
             // tile of half the size costs 6 % of the whole scan; measured: wins up to k ~ 72, beyond
             // that twice as many CTAs per query with long lists of their own cost more)
             for (int in_smem = 1; in_smem >= 0 && !qt_cap; --in_smem) {
-                if (!in_smem && !(e->list_ws_opt && K <= e->list_ws_kmax && qtry == qt_max && qtry >= 128 && vp->ctas == 1 && !vp->staged)) break;
+                if (!in_smem && !(e->list_ws_opt && K <= e->list_ws_kmax && qtry == qt_max && qtry >= 128 && vp->ctas == 1 && !vp->staged())) break;
                 for (int ci = 0; ci < 4 && !qt_cap; ++ci) {
                     const int ctry = std::min(1024, (caps[ci] + 31) / 32 * 32);
                     if (ctry > 0 && scan_smem_bytes(qtry, ctry, K, stage_bytes, in_smem != 0) <= smem_budget) {
@@ -410,7 +416,7 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     const int qt = (gsize + nqt0 - 1) / nqt0;
     const int nqt = (gsize + qt - 1) / qt;
     if (!lists_in_smem && scan_smem_bytes(qt, cap, K, stage_bytes, true) <= (size_t)216 * 1024 / v.ctas) lists_in_smem = true;  // few queries: they fit after all
-    if (v.dynamic && v.staged && nqt > e->sm_count * v.ctas) return fail(e, SR_EINVAL, "kernel shape %s: %d query tiles exceed the grid; raise the \"qt\" option", v.name, nqt);
+    if (v.dynamic && v.staged() && nqt > e->sm_count * v.smem_ctas()) return fail(e, SR_EINVAL, "kernel shape %s: %d query tiles exceed the grid; raise the \"qt\" option", v.name, nqt);
     e->last_lists_in_smem = lists_in_smem ? 1 : 0;
     const size_t smem = scan_smem_bytes(qt, cap, K, stage_bytes, lists_in_smem);
     int ctas = 0;

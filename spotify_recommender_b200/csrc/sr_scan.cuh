@@ -35,7 +35,10 @@
 //     still matter to the per-query pool -- and, in the DYN shapes, the exact keys of the hits
 //     still unsettled at that point, scored 32 at a time across all of a warp's queries;
 //     finalize_kernel merges the pool into the ordered top-K.
-//   bound pass (bound_kernel, before the scan): starting thresholds at filter speed.
+//   bound pass (bound_kernel, before the scan): starting thresholds at filter speed -- this
+//     store's own, or (row shards of one store) from block maxima max-reduced across the shards,
+//     which bound the K-th best of the WHOLE store: a shard's list may then end up shorter than K.
+//   ceilings (a.ceil): pass p > 0 of a K > 1024 query admits only keys below the last key of pass p - 1.
 //
 // The filter only ever discards pairs that provably are not in the exact top-K,
 // so results are bit-identical to the oracle whatever the thresholds were.
@@ -92,10 +95,10 @@ struct ScanArgs {
     unsigned long long *stats;  // [0] hits [1] settles [2] rescans [3] rescored [4] refilters; [5..12] cycle counters (-DSR_SCAN_TIMING)
 };
 
-// `stage_bytes`: size of the TMA staging buffer for one song tile (0 for unstaged shapes)
+// `stage_bytes`: size of the TMA staging buffers (0 for unstaged shapes)
 __host__ __device__ inline size_t scan_smem_bytes(int qt, int cap, int K, size_t stage_bytes = 0, bool lists_in_smem = true)
 {
-    return (stage_bytes ? stage_bytes + 16 : 0) + (lists_in_smem ? (size_t)qt * K * 8 : 0) + (size_t)qt * (kF + 10 + cap) * 4 + 48;
+    return (stage_bytes ? stage_bytes + 16 : 0) + (lists_in_smem ? (size_t)qt * K * 8 : 0) + (size_t)qt * (kF + 10 + cap) * 4 + 64;
 }
 
 // ---- TMA (bulk async copy) staging of song tiles: global -> shared, completion on an mbarrier
@@ -447,10 +450,15 @@ __device__ __forceinline__ uint32_t filter_query(const float2 (&fp)[S / 2][kF], 
 // one at a time from a per-query-tile counter (the claim for the tile after next is issued
 // before the current tile's arithmetic, so its latency is hidden).  CTAs that meet clusters,
 // ties or many settles simply claim fewer tiles: measured SM idle time at the end of a launch
-// drops from 9 % to ~1 %.
-template <int S, int THREADS, int MINB, bool DEFER, bool STAGE, bool DYN>
+// drops from 9 % to ~1 % (large batches) and from 23 % to ~3 % (16 queries, STAGE + DYN).
+// STAGE + DYN: the tile the bulk copy fetches next is the one claimed a tile ago (s_next), and a
+// CTA that joins another query tile starts that tile's first copy itself.
+// The shapes the engine selects (sr_engine.cu, kVariants; template <S, THREADS, CTAs/SM, DEFER, staging buffers, DYN>).
+template <int S, int THREADS, int MINB, bool DEFER, int NB, bool DYN>
 __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 {
+    constexpr bool STAGE = NB > 0;  // NB: TMA staging buffers per CTA (0: tiles go straight into registers)
+    static_assert(NB <= 1 || DYN, "two staging buffers need the dynamic claim ring");
     constexpr int TS = S * THREADS;
     constexpr int WARPS = THREADS / 32;
     constexpr int SUB = THREADS / kLT;  // layout tiles per CTA tile
@@ -461,10 +469,17 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr uint32_t kTileBytes = (uint32_t)TS * kF * 4;
-    float4 *s_tile = reinterpret_cast<float4 *>(smem_raw);                         // STAGE only
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + kTileBytes);          // STAGE only
+    // TWO staging buffers (one CTA per SM then: 2 x 96 KB): the copy of tile t + 2 starts the moment tile t has left its
+    // buffer, so a copy is in flight at every moment of the CTA's life and the arithmetic never waits for one that was
+    // issued too late (two single-buffered CTAs per SM fall into step with each other: both wait, then both compute).
+    // (Compiled with MINB = 2 although only one such CTA fits an SM: without the 128-register cap ptxas keeps the query
+    // operands of the hot loop in ordinary registers -- 0 of 768 FFMA2 with a uniform-register operand at 245 registers.)
+    constexpr int NBUF = NB > 1 ? 2 : 1;
+    constexpr int NS = NBUF + 2;  // DYN: ring of claimed tiles -- the current one, the next NBUF (already known), the one being claimed
+    float4 *s_tile = reinterpret_cast<float4 *>(smem_raw);                                 // STAGE only: [NBUF] tiles
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + NBUF * kTileBytes);           // STAGE only: [NBUF]
     QueryCtx c;
-    c.list = reinterpret_cast<uint64_t *>(smem_raw + (STAGE ? kTileBytes + 16 : 0));
+    c.list = reinterpret_cast<uint64_t *>(smem_raw + (STAGE ? NBUF * kTileBytes + 16 : 0));
     c.qraw = reinterpret_cast<float *>(c.list + (a.list_ws ? 0 : (size_t)a.qt * a.K));
     if (a.list_ws) c.list = a.list_ws + (size_t)blockIdx.x * a.qt * a.K;
     c.nthr = c.qraw + a.qt * kF;
@@ -483,7 +498,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     int *s_flag = reinterpret_cast<int *>(c.hit + (size_t)a.qt * a.cap);
     int *s_redo_cnt = s_flag + 4;                 // [2]
     int *s_redo = s_redo_cnt + 4;                 // [2][qt] queries whose tile must be re-filtered
-    int *s_next = s_redo + 2 * a.qt;              // DYN: [0..2] claimed song tiles (this one and the next two), [3] next query tile
+    int *s_next = s_redo + 2 * a.qt;              // DYN: [0..NS-1] claimed song tiles (a ring: this one and the next NS - 2), [NS] next query tile
     // DYN: the per-tile barrier is split (arrive ... wait) so the next tile's loads overlap the wait
     __shared__ uint64_t s_tbar;
     uint32_t tbar_phase = 0;
@@ -513,8 +528,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         else while (bb >= a.cpq) { bb -= a.cpq; ++qtile; }
         u = 0; u_end = 1; t0 = 0;
         if (tid == 0) {
-            s_next[0] = atomicAdd(a.tile_ctr + qtile, 1);
-            s_next[1] = atomicAdd(a.tile_ctr + qtile, 1);
+            for (int i = 0; i < NS - 1; ++i) s_next[i] = atomicAdd(a.tile_ctr + qtile, 1);
             mbar_init(&s_tbar, WARPS);
         }
     } else {
@@ -523,10 +537,13 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
     uint32_t sphase = 0;
     if (STAGE) {
         if (tid == 0) {
-            mbar_init(s_bar, 1);
-            // (DYN: the first claimed tile; a claim at or beyond n_tiles means the query tile is already exhausted)
-            const int first = DYN ? s_next[0] : t0;
-            if (u < u_end && first < a.n_tiles) tma_load_tile(s_tile, a.hat + (int64_t)first * a.tile_stride * (TS * kF), kTileBytes, s_bar);
+            // (DYN: the first claimed tile(s); a claim at or beyond n_tiles means the query tile is already exhausted)
+            for (int b = 0; b < NBUF; ++b) {
+                mbar_init(s_bar + b, 1);
+                const int first = DYN ? s_next[b] : t0;
+                if (u < u_end && first < a.n_tiles)
+                    tma_load_tile(s_tile + (size_t)b * (kTileBytes / 16), a.hat + (int64_t)first * a.tile_stride * (TS * kF), kTileBytes, s_bar + b);
+            }
         }
         __syncthreads();
     }
@@ -578,7 +595,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
         // its songs are loaded between arriving at tile t's barrier and waiting on it.
         int tile = DYN ? __reduce_max_sync(0xffffffffu, s_next[0]) : t0;
         if (DYN && !STAGE) load_songs(min(tile, a.n_tiles - 1));
-        for (; tile < t1; ++it, slot = (slot == 2 ? 0 : slot + 1)) {
+        for (; tile < t1; ++it, slot = (slot == NS - 1 ? 0 : slot + 1)) {
             // (the claim for the tile after next: issued now, stored after the hot loop, so thread 0
             // does not start every tile a global round trip late)
             int claimed = 0;
@@ -587,7 +604,7 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 // the next tile of this CTA (claimed one tile ago) starts its way from HBM into L2 now, so the loads
                 // issued between this tile's arrive and wait find it there: with few queries per tile (mid-size
                 // batches) the tile load is otherwise 15-25 % of the tile's time.  One slice per warp.
-                const int nt = s_next[slot == 2 ? 0 : slot + 1];
+                const int nt = s_next[slot == NS - 1 ? 0 : slot + 1];
                 if (nt < a.n_tiles) {
                     const char *src = reinterpret_cast<const char *>(a.hat) + ((int64_t)nt * a.tile_stride * TS * kF * 4) + (size_t)warp * (kTileBytes / WARPS);
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(kTileBytes / WARPS) : "memory");
@@ -598,9 +615,10 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             const int row0 = (int)(ltile * (S * kLT)) + tid % kLT;  // its songs: row0 + s * kLT (ids are 32-bit)
 
             if (STAGE) {
-                mbar_wait(s_bar, sphase);  // this tile has landed in shared memory
-                sphase ^= 1u;
-                const float4 *src = s_tile + ((tid / kLT) * (S / 2) * kLT + tid % kLT) * 6;
+                const int buf = NBUF == 2 ? (it & 1) : 0;
+                mbar_wait(s_bar + buf, (sphase >> buf) & 1u);  // this tile has landed in shared memory
+                sphase ^= 1u << buf;
+                const float4 *src = s_tile + (size_t)buf * (kTileBytes / 16) + ((tid / kLT) * (S / 2) * kLT + tid % kLT) * 6;
 #pragma unroll
                 for (int p = 0; p < S / 2; ++p) {
 #pragma unroll
@@ -615,12 +633,12 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                 __syncthreads();  // every thread has copied its songs out: the buffer is free
                 if (tid == 0) {   // next tile of this run: same query tile, or tile 0 of the next one
                     int64_t nxt = -1;
-                    if (DYN) {    // (claimed one tile ago; at or beyond n_tiles: this query tile is exhausted)
-                        const int nt = s_next[slot == 2 ? 0 : slot + 1];
+                    if (DYN) {    // (the tile NBUF ahead, claimed a tile ago; at or beyond n_tiles: this query tile is exhausted)
+                        const int nt = s_next[(slot + NBUF) % NS];
                         if (nt < a.n_tiles) nxt = (int64_t)nt * a.tile_stride;
                     } else if (tile + 1 < t1) nxt = stile + a.tile_stride;
                     else if (u + (t1 - t0) < u_end) nxt = 0;
-                    if (nxt >= 0) tma_load_tile(s_tile, a.hat + nxt * (TS * kF), kTileBytes, s_bar);
+                    if (nxt >= 0) tma_load_tile(s_tile + (size_t)buf * (kTileBytes / 16), a.hat + nxt * (TS * kF), kTileBytes, s_bar + buf);
                 }
             } else if (!DYN) {
                 load_songs(tile);
@@ -704,8 +722,8 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
             };
             int next_tile = tile + 1;
             if (DYN) {
-                if (tid == 0) s_next[slot == 0 ? 2 : slot - 1] = claimed;  // (claimed at the top of the tile)
-                next_tile = __reduce_max_sync(0xffffffffu, s_next[slot == 2 ? 0 : slot + 1]);
+                if (tid == 0) s_next[slot == 0 ? NS - 1 : slot - 1] = claimed;  // (claimed at the top of the tile)
+                next_tile = __reduce_max_sync(0xffffffffu, s_next[slot == NS - 1 ? 0 : slot + 1]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_tbar);
                 // in flight while the slower warps finish: the next tile's songs (unless the bulk-copy engine is
@@ -874,16 +892,18 @@ __global__ void __launch_bounds__(THREADS, MINB) scan_kernel(const ScanArgs a)
                     c2 = (c2 + 1 == nqt_d) ? 0 : c2 + 1;
                     if (*(volatile int *)(a.tile_ctr + c2) < a.n_tiles && atomicAdd(a.visit_ctr + c2, 1) < a.steal_max) cand = c2;
                 }
-                s_next[3] = cand;
+                s_next[NS] = cand;
                 if (cand >= 0) {
-                    const int first = atomicAdd(a.tile_ctr + cand, 1);
-                    s_next[0] = first;
-                    s_next[1] = atomicAdd(a.tile_ctr + cand, 1);
-                    if (STAGE && first < a.n_tiles) tma_load_tile(s_tile, a.hat + (int64_t)first * a.tile_stride * (TS * kF), kTileBytes, s_bar);
+                    for (int i = 0; i < NS - 1; ++i) s_next[i] = atomicAdd(a.tile_ctr + cand, 1);
+                    if (STAGE) {
+                        for (int b = 0; b < NBUF; ++b)
+                            if (s_next[b] < a.n_tiles)
+                                tma_load_tile(s_tile + (size_t)b * (kTileBytes / 16), a.hat + (int64_t)s_next[b] * a.tile_stride * (TS * kF), kTileBytes, s_bar + b);
+                    }
                 }
             }
             __syncthreads();
-            const int cand = __reduce_max_sync(0xffffffffu, s_next[3]);
+            const int cand = __reduce_max_sync(0xffffffffu, s_next[NS]);
             SR_TIME_END(6);
             if (cand < 0) break;
             qtile = cand;

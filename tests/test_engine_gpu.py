@@ -79,7 +79,7 @@ def test_golden_vectors(eng, oracle, case):
             assert np.array_equal(gs[0, :n].view(np.uint32), ref_sc[gi[0, :n]].view(np.uint32))
 
 
-@pytest.mark.parametrize("variant", range(9))
+@pytest.mark.parametrize("variant", range(10))
 def test_every_kernel_shape(eng, oracle, variant):  # k = 1, 10, 100; 257 queries
     n = 150_000
     f = synth.features(n)

@@ -12,8 +12,8 @@ import pytest
 from spotify_recommender_b200 import build
 
 # scan_kernel<S, THREADS, CTAs/SM, DEFER, STAGE, DYN>: the small-batch (TMA-staged) and large-batch (dynamic) shapes
-AUTO_SHAPES = {"small-batch S8xT256x2-dyn-tma": "ILi8ELi256ELi2ELb1ELb1ELb1E", "mid-batch S8xT256x2-dyn": "ILi8ELi256ELi2ELb1ELb0ELb1E",
-               "large-batch S8xT512x1-dyn": "ILi8ELi512ELi1ELb1ELb0ELb1E"}
+AUTO_SHAPES = {"small-batch S8xT256x2-dyn-tma": "ILi8ELi256ELi2ELb1ELi1ELb1E", "mid-batch S8xT256x2-dyn": "ILi8ELi256ELi2ELb1ELi0ELb1E",
+               "large-batch S8xT512x1-dyn": "ILi8ELi512ELi1ELb1ELi0ELb1E"}
 
 
 @pytest.fixture(scope="module")
