@@ -150,21 +150,27 @@ class QueryShardedAllPairs:
         return self.engine.all_pairs_topk(lo, hi, k)
 
     def gather_table(self, li: np.ndarray, ls: np.ndarray):
-        """The one exchange of the path: every rank's slice -> the whole N x k table on every rank."""
+        """The one exchange of the path: every rank's slice -> the whole N x k table on every rank.  Indices and
+        score bits travel as ONE int32 array (one all-gather), staged through pinned memory on GPUs."""
         if self.world == 1:
             return li, ls
         k = li.shape[1]
         per = -(-self.n // self.world)
-        pad_i = torch.full((per, k), -1, dtype=torch.int32)
-        pad_s = torch.zeros((per, k), dtype=torch.float32)
-        pad_i[:li.shape[0]] = torch.from_numpy(li)
-        pad_s[:ls.shape[0]] = torch.from_numpy(ls)
-        d_i, d_s = pad_i.to(self.device), pad_s.to(self.device)
-        all_i = torch.empty((self.world * per, k), dtype=torch.int32, device=self.device)
-        all_s = torch.empty((self.world * per, k), dtype=torch.float32, device=self.device)
-        dist.all_gather_into_tensor(all_i, d_i, group=self.group)
-        dist.all_gather_into_tensor(all_s, d_s, group=self.group)
-        return all_i[:self.n].cpu().numpy(), all_s[:self.n].cpu().numpy()
+        cuda = self.device.type == "cuda"
+        loc = torch.empty((per, 2 * k), dtype=torch.int32, pin_memory=cuda)
+        loc[:, :k] = -1
+        loc[:, k:] = 0
+        loc[:li.shape[0], :k] = torch.from_numpy(li)
+        loc[:ls.shape[0], k:] = torch.from_numpy(ls.view(np.int32))
+        d_loc = loc.to(self.device, non_blocking=True)
+        d_all = torch.empty((self.world * per, 2 * k), dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(d_all, d_loc, group=self.group)
+        h_all = torch.empty((self.n, 2 * k), dtype=torch.int32, pin_memory=cuda)
+        h_all.copy_(d_all[:self.n], non_blocking=True)
+        if cuda:
+            torch.cuda.current_stream().synchronize()
+        a = h_all.numpy()
+        return np.ascontiguousarray(a[:, :k]), np.ascontiguousarray(a[:, k:]).view(np.float32)
 
     def all_pairs_topk(self, k: int):
         """(idx[N,k] int32, score[N,k] f32) host arrays, identical on every rank."""
