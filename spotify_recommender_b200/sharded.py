@@ -150,21 +150,23 @@ class QueryShardedAllPairs:
         return self.engine.all_pairs_topk(lo, hi, k)
 
     def gather_table(self, li: np.ndarray, ls: np.ndarray):
-        """The one exchange of the path: every rank's slice -> the whole N x k table on every rank.  Indices and
-        score bits travel as ONE int32 array (one all-gather)."""
+        """The one exchange of the path: every rank's slice -> the whole N x k table on every rank.
+        (Indices and scores stay two contiguous arrays: packing them into one for a single all-gather was measured
+        slower -- the strided host copies of an 80 MB table cost more than the second collective.)"""
         if self.world == 1:
             return li, ls
         k = li.shape[1]
         per = -(-self.n // self.world)
-        loc = torch.empty((per, 2 * k), dtype=torch.int32)
-        loc[:, :k] = -1
-        loc[:, k:] = 0
-        loc[:li.shape[0], :k] = torch.from_numpy(li)
-        loc[:ls.shape[0], k:] = torch.from_numpy(ls.view(np.int32))
-        d_all = torch.empty((self.world * per, 2 * k), dtype=torch.int32, device=self.device)
-        dist.all_gather_into_tensor(d_all, loc.to(self.device), group=self.group)
-        a = d_all[:self.n].cpu().numpy()  # (a one-off 80 MB copy at 1 M songs: pinning a buffer for it costs more than it saves)
-        return np.ascontiguousarray(a[:, :k]), np.ascontiguousarray(a[:, k:]).view(np.float32)
+        pad_i = torch.full((per, k), -1, dtype=torch.int32)
+        pad_s = torch.zeros((per, k), dtype=torch.float32)
+        pad_i[:li.shape[0]] = torch.from_numpy(li)
+        pad_s[:ls.shape[0]] = torch.from_numpy(ls)
+        d_i, d_s = pad_i.to(self.device), pad_s.to(self.device)
+        all_i = torch.empty((self.world * per, k), dtype=torch.int32, device=self.device)
+        all_s = torch.empty((self.world * per, k), dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(all_i, d_i, group=self.group)
+        dist.all_gather_into_tensor(all_s, d_s, group=self.group)
+        return all_i[:self.n].cpu().numpy(), all_s[:self.n].cpu().numpy()
 
     def all_pairs_topk(self, k: int):
         """(idx[N,k] int32, score[N,k] f32) host arrays, identical on every rank."""
