@@ -142,9 +142,13 @@ def cpu_baseline_port(feats: np.ndarray, n_total: int, k: int, batch: int, budge
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    o.query_index(feats, q[:2], k, threads=1)  # the same code on ONE host thread (both are reported)
+    dt1 = time.perf_counter() - t1
     return {"value": done * float(feats.shape[0]) / dt, "unit": "song-pairs/s", "cores": cores, "kind": "port",
             "sample": f"{done} of the batch's {batch} queries x {feats.shape[0]} songs, top-{k}, "
-                      f"oracle/cosine_topk_oracle.c with {cores} OpenMP threads, {dt:.1f} s"}
+                      f"oracle/cosine_topk_oracle.c with {cores} OpenMP threads, {dt:.1f} s",
+            "value_single_thread": 2 * float(feats.shape[0]) / dt1, "single_thread_sample": f"2 queries x {feats.shape[0]} songs, 1 thread, {dt1:.2f} s"}
 
 
 def run_reference(args) -> None:
