@@ -64,7 +64,8 @@ struct Variant {
     int nbuf;              // TMA staging buffers per CTA (0: tiles are loaded straight into registers)
     bool dynamic;
     bool staged() const { return nbuf > 0; }
-    int smem_ctas() const { return nbuf == 2 ? 1 : ctas; }  // CTAs per SM the shared-memory budget is shared by
+    // CTAs per SM the shared-memory budget is shared by: one when the staging buffers alone exceed half an SM's shared memory
+    int smem_ctas() const { return (size_t)nbuf * S * threads * kF * 4 > (size_t)110 * 1024 ? 1 : ctas; }
     ScanLaunch launch;
     ScanOcc occ;
     BoundLaunch bound;
@@ -78,7 +79,7 @@ struct Variant {
 #define SR_VARIANT_DTMA(S, T, M) \
     {"S" #S "xT" #T "x" #M "-dyn-tma", S, T, M, 1, true, launch_scan<S, T, M, true, 1, true>, occ_scan<S, T, M, true, 1, true>, launch_bound<S, T, M>}
 #define SR_VARIANT_DTMA2(S, T, M) \
-    {"S" #S "xT" #T "x1-dyn-tma2", S, T, M, 2, true, launch_scan<S, T, M, true, 2, true>, occ_scan<S, T, M, true, 2, true>, launch_bound<S, T, M>}
+    {"S" #S "xT" #T "-dyn-tma2", S, T, M, 2, true, launch_scan<S, T, M, true, 2, true>, occ_scan<S, T, M, true, 2, true>, launch_bound<S, T, M>}
 const Variant kVariants[] = {
     SR_VARIANT(8, 256, 2, false),   // 0  plain hit branch in the loop
     SR_VARIANT(8, 256, 2, true),    // 1  branch-free loop, deferred hits
@@ -91,6 +92,9 @@ const Variant kVariants[] = {
     SR_VARIANT_TMA(8, 256, 2),      // 7  the static form of 4 (contiguous runs of units)
     SR_VARIANT_DYN(8, 256, 2),      // 8  mid-size batches, short lists: two 256-thread CTAs per SM loading straight into registers
     SR_VARIANT_DTMA2(8, 256, 2),    // 9  one 256-thread CTA per SM with TWO TMA staging buffers (a copy in flight at every moment)
+    // (tried and dropped: SR_VARIANT_DTMA2(4, 256, 2) -- 4 songs per thread, two CTAs per SM, two 48 KB staging buffers each: with
+    // half the registers taken by songs ptxas keeps the query operands in ordinary registers (LDC, not LDCU): 1 query 74.8 us
+    // (0.994 of the copy bandwidth) but 16 queries 119 us against 99 us.)
     // (tried and dropped: SR_VARIANT_DTMA(4, 256, 3) -- 4 songs per thread, three CTAs per SM, 49 KB TMA stages, on the SAME
     // store (an 8-song layout tile is two contiguous 4-song layout tiles).  At 85 registers ptxas keeps none of the FFMA2 query
     // operands in uniform registers and the shape loses from 8 queries up: 16 queries 118 us against 99 us.)
