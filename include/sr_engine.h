@@ -17,7 +17,8 @@
  *     of a larger store answers with ids of the whole store.
  *   - results are ordered by (score descending, id ascending); rows shorter
  *     than k are padded with id -1 / score 0.  Scores are bit-identical to the
- *     reference's CPU arithmetic (Recommender.cu:256-273).
+ *     reference's CPU arithmetic (Recommender.cu:256-273); the one exception is
+ *     that a score of -0.0 (only non-finite inputs produce one) is returned as +0.0.
  *   - any k >= 1: like the reference (Recommender.cu:300-315) a query yields
  *     min(k, songs - 1) results.  Lists longer than 1024 are produced 1024 at a
  *     time (one more pass over the store each, every pass continuing below the
