@@ -99,3 +99,29 @@ def test_random_sharded_case_equals_oracle(oracle, seed):
         got = se.query_by_index(q, k)
     assert np.array_equal(got[0], want[0]), (n, nq, k, kind, shards, np.argwhere(got[0] != want[0])[:3])
     assert same_scores(got[1], want[1]), (n, nq, k, kind, shards)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_vector_queries_on_a_row_shard(oracle, seed):
+    """query_by_vector on a shard with an id base: arbitrary (also hostile) query rows, exclusions inside and
+    outside the shard, against the oracle's query_rows."""
+    from spotify_recommender_b200.engine import Engine
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.choice([50, 4096, 30_000, 120_000]))
+    base = int(rng.choice([0, 1, 777_777, 2_000_000_000]))
+    nq = int(rng.choice([1, 3, 40, 300, 1500]))
+    k = int(rng.choice([1, 10, 40, 100, 500, 1030]))
+    f = _data(rng, str(rng.choice(["features", "uniform", "clustered", "hostile"])), n)
+    qv = _data(rng, str(rng.choice(["uniform", "hostile"])), nq)
+    qv[rng.integers(0, nq)] = f[rng.integers(0, n)]          # one query IS a song of the store
+    if rng.random() < 0.5:
+        qv[rng.integers(0, nq)] = 0.0                          # a zero query: every score 0, order by id
+    ex = rng.integers(base - 5, base + n + 5, nq).astype(np.int64)
+    ex[rng.random(nq) < 0.3] = -1
+    ex_local = np.where((ex >= base) & (ex < base + n), ex - base, -1)
+    want = oracle.query_rows(f, qv, ex_local, k, id_base=base, threads=8)
+    with Engine(0) as e:
+        e.load_features(f, id_base=base)
+        got = e.query_by_vector(qv, k, exclude=ex.astype(np.int32))
+    assert np.array_equal(got[0], want[0]), (n, base, nq, k, np.argwhere(got[0] != want[0])[:3])
+    assert same_scores(got[1], want[1]), (n, base, nq, k)
