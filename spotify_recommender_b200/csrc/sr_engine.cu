@@ -465,7 +465,10 @@ int run_pass(sr_engine *e, const int32_t *d_qidx, const float *d_qrows, const in
     const int n_sample = shared ? (int)std::min<int64_t>(std::max<int64_t>(1, (want_tiles + out.sample_div - 1) / std::max(1, out.sample_div)), full_tiles)
                                 : (int)std::min<int64_t>({want_tiles, std::max<int64_t>(4, full_tiles / (e->bound_cap_div > 0 ? e->bound_cap_div : 16)), full_tiles / 4});
     const bool use_bound = shared ? (out.blocks_out != nullptr) : (e->bound && !out.ceil_in && K + 1 <= nblk && nblk <= kLT && n_sample >= 4 && (int64_t)n_sample * TS >= 16 * (int64_t)nblk);
-    const int bqt = std::max(1, std::min({qt, 64, (int)(48 * 1024 / (nblk * 4))}));  // the bound pass's own (finer) query tiles: the block maxima of a tile live in shared memory
+    // the bound pass's own (finer) query tiles: the block maxima of a tile live in shared memory.  (Larger tiles -- 64 ... 160
+    // queries with 256 blocks -- were measured SLOWER, 525 -> 545 ... 655 us per 4096-query top-100 batch: the shared-memory
+    // atomics and the flush, not the sample tile's load, are what the pass spends its time on.)
+    const int bqt = std::max(1, std::min({qt, 64, (int)(48 * 1024 / (nblk * 4))}));
     const int bnqt_max = (gsize + bqt - 1) / bqt;
 
     int rc;
